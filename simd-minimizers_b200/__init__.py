@@ -1,0 +1,412 @@
+"""simd-minimizers_b200 -- B200-native random-minimizer path behind the simd-minimizers API.
+
+Host-side mirror (Python, over the C ABI in include/mz_b200.h) of the reference crate's public
+interface for this path (rust-seq/simd-minimizers v3.0.0, src/lib.rs:225-654):
+
+    minimizer_positions(seq, k, w)              canonical_minimizer_positions(seq, k, w)
+    minimizers(k, w) / canonical_minimizers(k, w)
+    closed_syncmers / canonical_closed_syncmers / open_syncmers / canonical_open_syncmers
+    canonical_syncmers (README name; alias of canonical_closed_syncmers)
+    Builder.hasher(h).super_kmers(sk).run(seq, pos) -> Output
+    Output.values_u64() / values_u128() / pos_and_values_u64() / pos_and_values_u128()
+
+Same names, argument meaning and error behaviour (the reference's assert!/panic! become
+``AssertionError`` with the reference's message).  All compute happens in hand-written
+sm_100a kernels inside libmzb200.so; nothing here computes a minimizer on the CPU.
+The package directory name contains a '-', so import it with
+``importlib.import_module("simd-minimizers_b200")``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+
+from . import _ffi
+from ._ffi import MzError, MzOut, MzParams, MzTiming
+
+__all__ = [
+    "PackedSeq", "PackedSeqVec", "NtHasher", "MulHasher", "U32Vec", "Builder", "Output",
+    "minimizers", "canonical_minimizers", "closed_syncmers", "canonical_closed_syncmers",
+    "open_syncmers", "canonical_open_syncmers", "canonical_syncmers", "minimizer_positions",
+    "canonical_minimizer_positions", "Context", "default_context", "MzError",
+]
+
+_PANICS = {2, 3, 4, 5, 6, 7}  # codes that are assert!/panic! in the reference
+
+
+def _check(code: int):
+    if code in _PANICS:
+        raise AssertionError(_ffi.lib().mz_strerror(code).decode())
+    _ffi.check(code)
+
+
+# ------------------------------------------------------------------------------------------
+# packed-seq stand-ins: just enough of PackedSeq / PackedSeqVec for this path
+# (packed-seq 5.0.0 is an external crate; layout: 4 bases per byte, first base in the low
+#  bits, A=0 C=1 T=2 G=3, see src/lib.rs:120-123)
+# ------------------------------------------------------------------------------------------
+_PAD = 16
+
+
+class PackedSeq:
+    """Borrowed view: bases [offset, offset+len) of a packed byte buffer."""
+
+    def __init__(self, data: np.ndarray, offset: int, length: int):
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        assert (offset + length + 3) // 4 <= data.size
+        self.data, self.offset, self.len = data, int(offset), int(length)
+
+    def __len__(self):
+        return self.len
+
+    def slice(self, start: int, end: int) -> "PackedSeq":
+        assert 0 <= start <= end <= self.len
+        return PackedSeq(self.data, self.offset + start, end - start)
+
+    def as_slice(self) -> "PackedSeq":
+        return self
+
+    def get(self, i: int) -> int:
+        p = self.offset + i
+        return (int(self.data[p >> 2]) >> (2 * (p & 3))) & 3
+
+    def to_revcomp(self) -> "PackedSeqVec":
+        p = np.arange(self.offset, self.offset + self.len, dtype=np.int64)
+        codes = (self.data[p >> 2] >> (2 * (p & 3)).astype(np.uint8)) & 3
+        return PackedSeqVec.from_codes((codes[::-1] ^ 2).astype(np.uint8))
+
+
+class PackedSeqVec:
+    """Owning packed sequence."""
+
+    def __init__(self, data: np.ndarray, length: int):
+        self.data, self.len = data, int(length)
+
+    @staticmethod
+    def from_codes(codes: np.ndarray) -> "PackedSeqVec":
+        n = int(codes.size)
+        padded = np.zeros((n + 3) // 4 * 4, dtype=np.uint8)
+        padded[:n] = codes
+        q = padded.reshape(-1, 4)
+        data = np.zeros((n + 3) // 4 + _PAD, dtype=np.uint8)
+        data[:q.shape[0]] = q[:, 0] | (q[:, 1] << 2) | (q[:, 2] << 4) | (q[:, 3] << 6)
+        return PackedSeqVec(data, n)
+
+    @staticmethod
+    def from_ascii(seq: bytes) -> "PackedSeqVec":
+        a = np.frombuffer(bytes(seq), dtype=np.uint8)
+        return PackedSeqVec.from_codes((a >> 1) & 3)
+
+    @staticmethod
+    def random(n: int, seed: int | None = None) -> "PackedSeqVec":
+        rng = np.random.default_rng(seed)
+        data = np.zeros((n + 3) // 4 + _PAD, dtype=np.uint8)
+        data[:(n + 3) // 4] = rng.integers(0, 256, size=(n + 3) // 4, dtype=np.uint8)
+        return PackedSeqVec(data, n)
+
+    def __len__(self):
+        return self.len
+
+    def as_slice(self) -> PackedSeq:
+        return PackedSeq(self.data, 0, self.len)
+
+    def slice(self, start: int, end: int) -> PackedSeq:
+        return self.as_slice().slice(start, end)
+
+
+# ------------------------------------------------------------------------------------------
+# hashers (seq-hash 0.2.0 NtHasher<RC> / MulHasher<RC>, passed to the device as tables)
+# ------------------------------------------------------------------------------------------
+class _TableHasher:
+    _setter = None
+
+    def __init__(self, k: int, canonical: bool = True):
+        self._k, self._canonical = int(k), bool(canonical)
+
+    @classmethod
+    def new(cls, k: int, canonical: bool = True):
+        return cls(k, canonical)
+
+    def k(self) -> int:
+        return self._k
+
+    def is_canonical(self) -> bool:
+        return self._canonical
+
+    def _apply(self, p: MzParams):
+        _check(getattr(_ffi.lib(), self._setter)(C.byref(p), int(self._canonical)))
+
+
+class NtHasher(_TableHasher):
+    _setter = "mz_params_set_nthash"
+
+
+class MulHasher(_TableHasher):
+    _setter = "mz_params_set_mulhash"
+
+
+# ------------------------------------------------------------------------------------------
+# context
+# ------------------------------------------------------------------------------------------
+class Context:
+    """Streams + device scratch for a set of GPUs (mz_ctx).  Not thread-safe: one per thread,
+    like the reference's thread_local CACHE (src/lib.rs:217-219)."""
+
+    def __init__(self, devices: list[int] | None = None):
+        self._h = C.c_void_p()
+        if devices:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(_ffi.lib().mz_ctx_create(arr, len(devices), C.byref(self._h)))
+        else:
+            _check(_ffi.lib().mz_ctx_create(None, 0, C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            _ffi.lib().mz_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def device_count(self) -> int:
+        return _ffi.lib().mz_ctx_device_count(self._h)
+
+    def last_timing(self) -> dict:
+        t = MzTiming()
+        _check(_ffi.lib().mz_last_timing(self._h, C.byref(t)))
+        return {"h2d_ms": t.h2d_ms, "kernel_ms": t.kernel_ms, "d2h_ms": t.d2h_ms,
+                "total_ms": t.total_ms, "kernel_launches": t.kernel_launches}
+
+
+_tls = threading.local()
+
+
+def default_context() -> Context:
+    ctx = getattr(_tls, "ctx", None)
+    if ctx is None:
+        ctx = _tls.ctx = Context()
+    return ctx
+
+
+# ------------------------------------------------------------------------------------------
+# Vec<u32> stand-in with append semantics
+# ------------------------------------------------------------------------------------------
+class U32Vec:
+    """Growable u32 vector (the caller's ``Vec<u32>``; results are *appended*, src/lib.rs:80)."""
+
+    def __init__(self, init=None):
+        self._a = np.zeros(0, dtype=np.uint32) if init is None else np.array(init, dtype=np.uint32)
+
+    def clear(self):
+        self._a = self._a[:0]
+
+    def __len__(self):
+        return int(self._a.size)
+
+    def __iter__(self):
+        return iter(self._a.tolist())
+
+    def __getitem__(self, i):
+        return self._a[i]
+
+    def last(self):
+        return int(self._a[-1]) if self._a.size else None
+
+    @property
+    def array(self) -> np.ndarray:
+        return self._a
+
+    def tolist(self):
+        return self._a.tolist()
+
+    def __eq__(self, other):
+        return self.tolist() == (other.tolist() if hasattr(other, "tolist") else list(other))
+
+    def _extend(self, arr: np.ndarray):
+        self._a = np.concatenate([self._a, arr.astype(np.uint32, copy=False)])
+
+
+def _as_vec(v):
+    if isinstance(v, U32Vec):
+        return v
+    raise TypeError("positions must be collected into a simd_minimizers U32Vec")
+
+
+# ------------------------------------------------------------------------------------------
+# Builder / Output  (src/lib.rs:225-630)
+# ------------------------------------------------------------------------------------------
+class Output:
+    """src/lib.rs:232-237, 579-630.  ``len`` is k for minimizers, k+w-1 for syncmers."""
+
+    def __init__(self, builder: "Builder", seq: PackedSeq, min_pos: U32Vec, start: int, vals64):
+        self.len = builder.k if builder.syncmer == 0 else builder.k + builder.w - 1
+        self._b, self.seq, self.min_pos, self._start, self._vals64 = builder, seq, min_pos, start, vals64
+
+    def _values(self, bits: int) -> np.ndarray:
+        if self.len > bits // 2:
+            raise AssertionError(_ffi.lib().mz_strerror(7).decode())
+        # Values cover *all* of min_pos (the reference iterates the whole Vec, src/lib.rs:599).
+        if bits == 64 and self._vals64 is not None and self._start == 0:
+            return self._vals64
+        if self._start != 0:
+            raise NotImplementedError("values of positions appended by an earlier run: call "
+                                      "U32Vec.clear() between runs")
+        _, _, vals = self._b._execute(self.seq, value_bits=bits)
+        return vals
+
+    def values_u64(self):
+        return self._values(64)
+
+    def values_u128(self):
+        v = self._values(128)
+        return [int(lo) | (int(hi) << 64) for lo, hi in v]
+
+    def pos_and_values_u64(self):
+        return list(zip(self.min_pos.tolist(), self._values(64).tolist()))
+
+    def pos_and_values_u128(self):
+        return list(zip(self.min_pos.tolist(), self.values_u128()))
+
+
+class Builder:
+    """Type-state builder of the reference (src/lib.rs:225-230): CANONICAL, hasher, SkPos,
+    SYNCMER are plain attributes here."""
+
+    def __init__(self, k: int, w: int, canonical: bool, syncmer: int, hasher=None, sk_pos=None,
+                 ctx: Context | None = None):
+        self.k, self.w, self.canonical, self.syncmer = int(k), int(w), bool(canonical), int(syncmer)
+        self._hasher, self._sk_pos, self._ctx = hasher, sk_pos, ctx
+
+    # -- configuration ------------------------------------------------------------------
+    def hasher(self, h) -> "Builder":
+        if self._sk_pos is not None:  # src/lib.rs:323-338: hasher() only before super_kmers()
+            raise TypeError("hasher() must be called before super_kmers()")
+        return Builder(self.k, self.w, self.canonical, self.syncmer, h, None, self._ctx)
+
+    def super_kmers(self, sk_pos: U32Vec) -> "Builder":
+        if self.syncmer != 0:  # src/lib.rs:339: only Builder<.., 0>
+            raise TypeError("super_kmers() is only available for minimizers")
+        return Builder(self.k, self.w, self.canonical, 0, self._hasher, _as_vec(sk_pos), self._ctx)
+
+    def context(self, ctx: Context) -> "Builder":
+        return Builder(self.k, self.w, self.canonical, self.syncmer, self._hasher, self._sk_pos, ctx)
+
+    # -- execution ----------------------------------------------------------------------
+    def _params(self, value_bits: int) -> MzParams:
+        p = MzParams()
+        L = _ffi.lib()
+        _check(L.mz_params_nthash(C.byref(p), self.k, self.w, self.syncmer, int(self.canonical)))
+        if self._hasher is not None:
+            if self._hasher.k() != self.k:
+                raise AssertionError("hasher.k() must equal the builder's k")
+            self._hasher._apply(p)
+        p.want_sk = 1 if self._sk_pos is not None else 0
+        p.value_bits = value_bits
+        return p
+
+    def _execute(self, seq, value_bits: int):
+        seq = seq.as_slice()
+        p = self._params(value_bits)
+        L = _ffi.lib()
+        n = seq.len
+        _check(L.mz_params_validate(C.byref(p), n))
+        l = self.k + self.w - 1
+        nwin = max(0, n - l + 1)
+        if self.syncmer == 0:
+            dens = 2.0 / (self.w + 1)
+        elif self.syncmer == 1:
+            dens = 1.0 if self.w == 1 else 2.0 / self.w
+        else:
+            dens = 1.0 / self.w
+        cap = int(min(nwin, nwin * dens * 1.25 + 4096))
+        ctx = self._ctx or default_context()
+        vw = value_bits // 64
+        while True:
+            pos = np.empty(max(cap, 1), dtype=np.uint32)
+            sk = np.empty(max(cap, 1), dtype=np.uint32) if p.want_sk else None
+            val = np.empty(max(cap, 1) * max(vw, 1), dtype=np.uint64) if vw else None
+            out = MzOut(pos.ctypes.data, sk.ctypes.data if sk is not None else None,
+                        val.ctypes.data if val is not None else None, cap, 0)
+            rc = L.mz_run(ctx.handle, C.byref(p), seq.data.ctypes.data, seq.offset, n, C.byref(out))
+            if rc == _ffi.MZ_ERR_CAPACITY:
+                cap = int(out.count)
+                continue
+            _check(rc)
+            break
+        m = int(out.count)
+        vals = None
+        if vw == 1:
+            vals = val[:m]
+        elif vw == 2:
+            vals = val[:2 * m].reshape(m, 2)
+        return pos[:m], (sk[:m] if sk is not None else None), vals
+
+    def run(self, seq, min_pos: U32Vec) -> Output:
+        """Append positions to ``min_pos`` (and super-k-mer starts to the sk vector)."""
+        min_pos = _as_vec(min_pos)
+        length = self.k if self.syncmer == 0 else self.k + self.w - 1
+        bits = 64 if length <= 32 else 0
+        pos, sk, vals = self._execute(seq, bits)
+        start = len(min_pos)
+        # SIMD-collector quirk (src/collect.rs:257,267): the first new element is dropped when
+        # it equals the caller's current last element.  Syncmers are appended verbatim
+        # (src/syncmers.rs:167-169).
+        if self.syncmer == 0 and start and pos.size and int(pos[0]) == min_pos.last():
+            pos, sk = pos[1:], (sk[1:] if sk is not None else None)
+            vals = vals[1:] if vals is not None else None
+        min_pos._extend(pos)
+        if self._sk_pos is not None:
+            self._sk_pos._extend(sk)
+        return Output(self, seq.as_slice(), min_pos, start, vals)
+
+    def run_once(self, seq) -> np.ndarray:
+        v = U32Vec()
+        self.run(seq, v)
+        return v.array
+
+
+def minimizers(k: int, w: int) -> Builder:                  # src/lib.rs:240
+    return Builder(k, w, False, 0)
+
+
+def canonical_minimizers(k: int, w: int) -> Builder:        # src/lib.rs:250
+    return Builder(k, w, True, 0)
+
+
+def closed_syncmers(k: int, w: int) -> Builder:             # src/lib.rs:269
+    return Builder(k, w, False, 1)
+
+
+def canonical_closed_syncmers(k: int, w: int) -> Builder:   # src/lib.rs:282
+    return Builder(k, w, True, 1)
+
+
+def open_syncmers(k: int, w: int) -> Builder:               # src/lib.rs:301
+    return Builder(k, w, False, 2)
+
+
+def canonical_open_syncmers(k: int, w: int) -> Builder:     # src/lib.rs:311
+    return Builder(k, w, True, 2)
+
+
+def canonical_syncmers(k: int, w: int) -> Builder:
+    """Name used by the reference docs (README.md:65, src/lib.rs:51) but absent from its code;
+    provided as an alias of canonical_closed_syncmers."""
+    return canonical_closed_syncmers(k, w)
+
+
+def minimizer_positions(seq, k: int, w: int) -> np.ndarray:             # src/lib.rs:639
+    return minimizers(k, w).run_once(seq)
+
+
+def canonical_minimizer_positions(seq, k: int, w: int) -> np.ndarray:   # src/lib.rs:652
+    return canonical_minimizers(k, w).run_once(seq)

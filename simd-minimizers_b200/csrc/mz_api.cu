@@ -1,0 +1,551 @@
+// mz_api.cu -- C ABI (include/mz_b200.h) over the sm_100a minimizer kernels.
+// Host side only orchestrates: shard windows over devices, copy, launch, gather.
+// There is deliberately no CPU implementation here.
+#include "../../include/mz_b200.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "mz_fast.cuh"
+#include "mz_generic.cuh"
+
+namespace {
+
+thread_local std::string g_last_error;
+
+int cuda_fail(cudaError_t e, const char* what, int line) {
+    char buf[512];
+    snprintf(buf, sizeof buf, "%s failed at mz_api.cu:%d: %s (%s)", what, line,
+             cudaGetErrorString(e), cudaGetErrorName(e));
+    g_last_error = buf;
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? MZ_ERR_NO_DEVICE
+                                                                       : MZ_ERR_CUDA;
+}
+#define CK(call)                                                   \
+    do {                                                           \
+        cudaError_t e__ = (call);                                  \
+        if (e__ != cudaSuccess) return cuda_fail(e__, #call, __LINE__); \
+    } while (0)
+
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t cap = 0;  // elements
+    int reserve(size_t n) {
+        if (n <= cap) return MZ_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 1024;
+        cudaError_t e = cudaMalloc(&p, want * sizeof(T));
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            e = cudaMalloc(&p, n * sizeof(T));
+            want = n;
+        }
+        if (e != cudaSuccess) return cuda_fail(e, "cudaMalloc", __LINE__);
+        cap = want;
+        return MZ_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostScalars {  // pinned
+    unsigned long long count;
+    uint32_t overflow;
+    uint32_t pad;
+};
+
+struct DevState {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    DevBuf<unsigned long long> scratch;  // [0]=count [1]=ticket|overflow [2..]=tile_state
+    DevBuf<uint8_t> in;
+    DevBuf<uint32_t> pos, sk;
+    DevBuf<uint64_t> val;
+    DevBuf<uint64_t> offs;  // batch CSR offsets
+    DevBuf<uint64_t> rstart;
+    DevBuf<uint32_t> rlen;
+    HostScalars* hs = nullptr;
+};
+
+}  // namespace
+
+struct mz_ctx {
+    std::vector<DevState> devs;
+    mz_timing timing{};
+};
+
+namespace {
+
+struct Plan {
+    bool fast = false;
+    uint32_t NT = 128, S = 32;
+    size_t smem = 0;
+    uint32_t num_tiles = 0;
+};
+
+uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
+
+size_t generic_smem(uint32_t NT, uint32_t S, uint32_t w, bool lr) {
+    size_t fixed = 16 * 8 + 8 * 4 + 40 * 4;
+    size_t per_thread = (size_t)((S + 31) / 32) * 4 + (size_t)S * 2 + (size_t)w * (lr ? 8 : 4);
+    return fixed + per_thread * NT;
+}
+
+// Choose launch geometry for a range of `nwin` windows (single sequence) on `d`.
+int plan_generic(const DevState& d, const mz_params& p, uint64_t nwin, Plan* pl) {
+    const bool lr = p.strand_tiebreak != 0;
+    const size_t budget = std::min<size_t>(d.smem_optin, 200 * 1024);
+    uint32_t NT = 128;
+    // shrink the block until a ring of w entries + 32 windows per thread fits
+    while (NT >= 32 && generic_smem(NT, 32, p.w, lr) > budget) NT /= 2;
+    if (NT < 32) return MZ_ERR_UNSUPPORTED;
+    // target ~4 tiles per SM, S in [32, 512], multiple of 32
+    uint64_t target_tiles = (uint64_t)d.sm_count * 4;
+    uint64_t s = (nwin + target_tiles * NT - 1) / (target_tiles * NT);
+    uint32_t S = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s, 32), 512);
+    S = round_up(S, 32);
+    while (S > 32 && generic_smem(NT, S, p.w, lr) > budget / 2) S -= 32;
+    if (S + p.w + 2 >= 65535) return MZ_ERR_UNSUPPORTED;
+    pl->fast = false;
+    pl->NT = NT;
+    pl->S = S;
+    pl->smem = generic_smem(NT, S, p.w, lr);
+    uint64_t T = (uint64_t)NT * S;
+    uint64_t tiles = (nwin + T - 1) / T;
+    if (tiles == 0 || tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
+    pl->num_tiles = (uint32_t)tiles;
+    return MZ_OK;
+}
+
+void fill_hash_args(mz::KArgs& a, const mz_params& p) {
+    a.k = p.k;
+    a.w = p.w;
+    a.l = p.k + p.w - 1;
+    a.mode = p.mode;
+    a.want_sk = p.want_sk ? 1u : 0u;
+    a.value_bits = p.value_bits;
+    a.val_len = p.mode == MZ_MODE_MINIMIZER ? p.k : p.k + p.w - 1;
+    a.val_canonical = p.strand_tiebreak ? 1u : 0u;
+    a.rot = p.rot;
+    for (int i = 0; i < 4; i++) a.f[i] = p.f[i], a.c[i] = p.c[i];
+}
+
+template <typename K>
+int set_smem(K kernel, size_t smem) {
+    if (smem > 48 * 1024) CK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    return MZ_OK;
+}
+
+int launch_generic(const mz_params& p, const Plan& pl, const mz::KArgs& a, cudaStream_t st) {
+    const bool hc = p.hash_canonical != 0, lr = p.strand_tiebreak != 0;
+    int rc;
+    if (hc && lr) {
+        if ((rc = set_smem(mz::mz_generic_kernel<true, true>, pl.smem))) return rc;
+        mz::mz_generic_kernel<true, true><<<pl.num_tiles, pl.NT, pl.smem, st>>>(a);
+    } else if (hc) {
+        if ((rc = set_smem(mz::mz_generic_kernel<true, false>, pl.smem))) return rc;
+        mz::mz_generic_kernel<true, false><<<pl.num_tiles, pl.NT, pl.smem, st>>>(a);
+    } else {
+        if ((rc = set_smem(mz::mz_generic_kernel<false, false>, pl.smem))) return rc;
+        mz::mz_generic_kernel<false, false><<<pl.num_tiles, pl.NT, pl.smem, st>>>(a);
+    }
+    CK(cudaGetLastError());
+    return MZ_OK;
+}
+
+// Enqueue one launch producing windows [wbeg, wend) on d.stream.  Input is already on the
+// device (a.seq etc. filled by the caller).  Scalars are copied to d.hs; caller synchronises.
+int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uint64_t wend,
+                uint32_t* launches) {
+    Plan pl;
+    int rc = mz::plan_fast(d.sm_count, d.smem_optin, p, wend - wbeg, &pl.NT, &pl.S, &pl.smem,
+                           &pl.num_tiles)
+                 ? (pl.fast = true, MZ_OK)
+                 : plan_generic(d, p, wend - wbeg, &pl);
+    if (rc) return rc;
+    if ((rc = d.scratch.reserve(2 + (size_t)pl.num_tiles))) return rc;
+    CK(cudaMemsetAsync(d.scratch.p, 0, (2 + (size_t)pl.num_tiles) * sizeof(unsigned long long), d.stream));
+    a.wbeg = wbeg;
+    a.wend = wend;
+    a.S = pl.S;
+    a.num_tiles = pl.num_tiles;
+    a.count_out = d.scratch.p;
+    a.ticket = reinterpret_cast<uint32_t*>(d.scratch.p + 1);
+    a.overflow = a.ticket + 1;
+    a.tile_state = d.scratch.p + 2;
+    if (pl.fast) rc = mz::launch_fast(p, pl.NT, pl.smem, pl.num_tiles, a, d.stream);
+    else rc = launch_generic(p, pl, a, d.stream);
+    if (rc > 0 && rc != MZ_OK) {
+        if (rc == MZ_ERR_CUDA && g_last_error.empty()) g_last_error = "kernel launch failed";
+        return rc;
+    }
+    if (launches) (*launches)++;
+    CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
+    return MZ_OK;
+}
+
+uint64_t estimate_capacity(const mz_params& p, uint64_t nwin) {
+    double dens;
+    if (p.mode == MZ_MODE_MINIMIZER) dens = 2.0 / (p.w + 1.0);
+    else if (p.mode == MZ_MODE_CLOSED_SYNCMER) dens = p.w == 1 ? 1.0 : 2.0 / p.w;
+    else dens = 1.0 / p.w;
+    double est = nwin * dens * 1.2 + 65536.0;
+    return (uint64_t)std::min<double>(est, (double)nwin);
+}
+
+int check_values(const mz_params& p) {
+    if (p.value_bits == 0) return MZ_OK;
+    if (p.value_bits != 64 && p.value_bits != 128) return MZ_ERR_BAD_ARG;
+    uint32_t len = p.mode == MZ_MODE_MINIMIZER ? p.k : p.k + p.w - 1;
+    if (len > p.value_bits / 2) return MZ_ERR_VALUE_WIDTH;
+    return MZ_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+uint32_t mz_abi_version(void) { return MZ_ABI_VERSION; }
+
+const char* mz_strerror(int code) {
+    switch (code) {
+        case MZ_OK: return "ok";
+        case MZ_ERR_BAD_ARG: return "bad argument";
+        case MZ_ERR_W_RANGE: return "w must satisfy 0 < w < 2^15 (sliding_min is not tested for windows of length > 2^15)";
+        case MZ_ERR_TOO_LONG: return "sliding_min returns 32bit indices. Try splitting the input into 4GB chunks first.";
+        case MZ_ERR_EVEN_L: return "Window length l=k+w-1 must be odd to guarantee canonicality";
+        case MZ_ERR_OPEN_EVEN_W: return "Open syncmers require odd window size, so that there is a unique middle element.";
+        case MZ_ERR_NOT_CANONICAL: return "canonical minimizers need a canonical hasher (hasher.is_canonical())";
+        case MZ_ERR_VALUE_WIDTH: return "k-mer (or l-mer for syncmers) does not fit the requested value width";
+        case MZ_ERR_CAPACITY: return "output capacity too small; mz_out.count holds the required size";
+        case MZ_ERR_UNSUPPORTED: return "parameter combination not supported by the B200 path";
+        case MZ_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+        case MZ_ERR_CUDA: return "CUDA error (see mz_last_error)";
+        case MZ_ERR_NOMEM: return "out of memory";
+        default: return "unknown error";
+    }
+}
+
+const char* mz_last_error(void) { return g_last_error.c_str(); }
+
+int mz_device_count(int* n) {
+    if (!n) return MZ_ERR_BAD_ARG;
+    *n = 0;
+    cudaError_t e = cudaGetDeviceCount(n);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *n = 0;
+        return cuda_fail(e, "cudaGetDeviceCount", __LINE__) == MZ_ERR_CUDA ? MZ_ERR_NO_DEVICE
+                                                                         : MZ_ERR_NO_DEVICE;
+    }
+    return *n > 0 ? MZ_OK : MZ_ERR_NO_DEVICE;
+}
+
+int mz_params_set_nthash(mz_params* p, uint32_t hash_canonical) {
+    if (!p) return MZ_ERR_BAD_ARG;
+    // seq-hash 0.2.0 NtHasher: low halves of the ntHash seeds, indexed by packed code A,C,T,G
+    static const uint32_t F[4] = {0x95c60474u, 0x62a02b4cu, 0x82572324u, 0x4be24456u};
+    for (int b = 0; b < 4; b++) p->f[b] = F[b], p->c[b] = F[b ^ 2];
+    p->rot = 7;
+    p->hash_canonical = hash_canonical ? 1u : 0u;
+    return MZ_OK;
+}
+
+int mz_params_set_mulhash(mz_params* p, uint32_t hash_canonical) {
+    if (!p) return MZ_ERR_BAD_ARG;
+    const uint32_t C = 0x27220a95u;  // low half of the FxHash multiplier
+    for (uint32_t b = 0; b < 4; b++) p->f[b] = b * C, p->c[b] = (b ^ 2u) * C;
+    p->rot = 7;
+    p->hash_canonical = hash_canonical ? 1u : 0u;
+    return MZ_OK;
+}
+
+static int params_init(mz_params* p, uint32_t k, uint32_t w, uint32_t mode, uint32_t canonical) {
+    if (!p) return MZ_ERR_BAD_ARG;
+    memset(p, 0, sizeof *p);
+    p->k = k;
+    p->w = w;
+    p->mode = mode;
+    p->strand_tiebreak = canonical ? 1u : 0u;
+    return MZ_OK;
+}
+
+int mz_params_nthash(mz_params* p, uint32_t k, uint32_t w, uint32_t mode, uint32_t canonical) {
+    int rc = params_init(p, k, w, mode, canonical);
+    return rc ? rc : mz_params_set_nthash(p, canonical);
+}
+
+int mz_params_mulhash(mz_params* p, uint32_t k, uint32_t w, uint32_t mode, uint32_t canonical) {
+    int rc = params_init(p, k, w, mode, canonical);
+    return rc ? rc : mz_params_set_mulhash(p, canonical);
+}
+
+int mz_params_validate(const mz_params* p, uint64_t n_bp) {
+    if (!p || p->k == 0 || p->mode > 2 || p->rot > 31) return MZ_ERR_BAD_ARG;
+    if (p->w == 0 || p->w >= (1u << 15)) return MZ_ERR_W_RANGE;
+    if (n_bp >= (1ull << 32)) return MZ_ERR_TOO_LONG;
+    if (p->strand_tiebreak && ((p->k + p->w - 1) & 1u) == 0) return MZ_ERR_EVEN_L;
+    if (p->strand_tiebreak && !p->hash_canonical) return MZ_ERR_NOT_CANONICAL;
+    if (p->mode == MZ_MODE_OPEN_SYNCMER && (p->w & 1u) == 0) return MZ_ERR_OPEN_EVEN_W;
+    if (p->want_sk && p->mode != MZ_MODE_MINIMIZER) return MZ_ERR_BAD_ARG;
+    return check_values(*p);
+}
+
+int mz_ctx_create(const int* device_ids, int n_devices, mz_ctx** out) {
+    if (!out || n_devices < 0) return MZ_ERR_BAD_ARG;
+    *out = nullptr;
+    int ndev = 0;
+    int rc = mz_device_count(&ndev);
+    if (rc) return rc;
+    std::vector<int> ids;
+    if (device_ids == nullptr || n_devices == 0) {
+        int cur = 0;
+        CK(cudaGetDevice(&cur));
+        ids.push_back(cur);
+    } else {
+        for (int i = 0; i < n_devices; i++) {
+            if (device_ids[i] < 0 || device_ids[i] >= ndev) return MZ_ERR_NO_DEVICE;
+            ids.push_back(device_ids[i]);
+        }
+    }
+    mz_ctx* ctx = new mz_ctx();
+    ctx->devs.resize(ids.size());
+    for (size_t i = 0; i < ids.size(); i++) {
+        DevState& d = ctx->devs[i];
+        d.device = ids[i];
+        cudaError_t e = cudaSetDevice(d.device);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+        for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable);
+        int v = 0;
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d.device);
+        d.sm_count = v;
+        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.device);
+        d.smem_optin = (size_t)v;
+        if (e != cudaSuccess) {
+            int code = cuda_fail(e, "context setup", __LINE__);
+            mz_ctx_destroy(ctx);
+            return code;
+        }
+    }
+    *out = ctx;
+    return MZ_OK;
+}
+
+void mz_ctx_destroy(mz_ctx* ctx) {
+    if (!ctx) return;
+    for (DevState& d : ctx->devs) {
+        cudaSetDevice(d.device);
+        if (d.stream) cudaStreamSynchronize(d.stream);
+        d.scratch.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
+        d.offs.release(), d.rstart.release(), d.rlen.release();
+        for (auto& e : d.ev)
+            if (e) cudaEventDestroy(e);
+        if (d.hs) cudaFreeHost(d.hs);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete ctx;
+}
+
+int mz_ctx_device_count(const mz_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+int mz_host_alloc(void** p, size_t bytes) {
+    if (!p) return MZ_ERR_BAD_ARG;
+    *p = nullptr;
+    CK(cudaHostAlloc(p, bytes ? bytes : 1, cudaHostAllocPortable));
+    return MZ_OK;
+}
+
+void mz_host_free(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+int mz_last_timing(const mz_ctx* ctx, mz_timing* t) {
+    if (!ctx || !t) return MZ_ERR_BAD_ARG;
+    *t = ctx->timing;
+    return MZ_OK;
+}
+
+int mz_run_device(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_packed,
+                  uint64_t bp_offset, uint64_t n_bp, uint64_t win_begin, uint64_t win_end,
+                  mz_out* out) {
+    if (!ctx || !p || !out || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return MZ_ERR_BAD_ARG;
+    int rc = mz_params_validate(p, n_bp);
+    if (rc) return rc;
+    out->count = 0;
+    const uint32_t l = p->k + p->w - 1;
+    if (n_bp < l) return MZ_OK;
+    const uint64_t nwin = n_bp - l + 1;
+    if (win_end == 0 || win_end > nwin) win_end = nwin;
+    if (win_begin >= win_end) return MZ_OK;
+    if (!d_packed || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
+
+    DevState& d = ctx->devs[dev_index];
+    CK(cudaSetDevice(d.device));
+    mz::KArgs a{};
+    fill_hash_args(a, *p);
+    // align the word pointer down to 4 bytes and fold the remainder into the bit bias
+    uintptr_t addr = reinterpret_cast<uintptr_t>(d_packed);
+    uintptr_t aligned = addr & ~uintptr_t(3);
+    a.seq = reinterpret_cast<const uint32_t*>(aligned);
+    a.bitbias = (int64_t)(8 * (addr - aligned) + 2 * bp_offset);
+    a.seq_nwords = ((uint64_t)a.bitbias + 2 * n_bp + 31) / 32;
+    a.nwin = nwin;
+    a.pos = out->pos;
+    a.sk = out->sk;
+    a.val = out->val;
+    a.cap = out->capacity;
+    ctx->timing = mz_timing{};
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    rc = enqueue_run(d, *p, a, win_begin, win_end, &ctx->timing.kernel_launches);
+    if (rc) return rc;
+    CK(cudaEventRecord(d.ev[1], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    CK(cudaEventElapsedTime(&ctx->timing.kernel_ms, d.ev[0], d.ev[1]));
+    ctx->timing.total_ms = ctx->timing.kernel_ms;
+    out->count = d.hs->count;
+    return d.hs->overflow ? MZ_ERR_CAPACITY : MZ_OK;
+}
+
+int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset,
+           uint64_t n_bp, mz_out* out) {
+    if (!ctx || !p || !out) return MZ_ERR_BAD_ARG;
+    int rc = mz_params_validate(p, n_bp);
+    if (rc) return rc;
+    out->count = 0;
+    const uint32_t l = p->k + p->w - 1;
+    if (n_bp < l) return MZ_OK;
+    if (!packed || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
+    const uint64_t nwin = n_bp - l + 1;
+    const size_t ndev = std::min<uint64_t>(ctx->devs.size(), nwin);
+    const uint32_t vw = p->value_bits / 64;  // u64 words per value
+    ctx->timing = mz_timing{};
+
+    struct Shard {
+        uint64_t wb, we, cap, count;
+    };
+    std::vector<Shard> sh(ndev);
+    const uint64_t per = (nwin + ndev - 1) / ndev;
+
+    // phase 1: H2D + kernel on every device
+    for (size_t i = 0; i < ndev; i++) {
+        DevState& d = ctx->devs[i];
+        Shard& s = sh[i];
+        s.wb = per * i;
+        s.we = std::min<uint64_t>(s.wb + per, nwin);
+        s.cap = estimate_capacity(*p, s.we - s.wb);
+        CK(cudaSetDevice(d.device));
+        // bases [blo, bhi) of the sequence are needed: one extra window on the left
+        const uint64_t blo = s.wb > 0 ? s.wb - 1 : 0;
+        const uint64_t bhi = s.we + l - 1;
+        const uint64_t byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
+        const uint64_t byte_hi = (bp_offset + bhi + 3) / 4;
+        const size_t nbytes = byte_hi - byte_lo;
+        if ((rc = d.in.reserve(nbytes + 64))) return rc;
+        if ((rc = d.pos.reserve(s.cap))) return rc;
+        if (p->want_sk && (rc = d.sk.reserve(s.cap))) return rc;
+        if (vw && (rc = d.val.reserve(s.cap * vw))) return rc;
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        CK(cudaMemcpyAsync(d.in.p, packed + byte_lo, nbytes, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaEventRecord(d.ev[1], d.stream));
+        mz::KArgs a{};
+        fill_hash_args(a, *p);
+        a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
+        a.bitbias = (int64_t)(2 * bp_offset) - (int64_t)(8 * byte_lo);
+        a.seq_nwords = (nbytes + 3) / 4;
+        a.nwin = nwin;
+        a.pos = d.pos.p;
+        a.sk = d.sk.p;
+        a.val = d.val.p;
+        a.cap = s.cap;
+        if ((rc = enqueue_run(d, *p, a, s.wb, s.we, &ctx->timing.kernel_launches))) return rc;
+        CK(cudaEventRecord(d.ev[2], d.stream));
+    }
+    // phase 2: counts; re-run a shard whose capacity estimate was too small
+    uint64_t total = 0;
+    for (size_t i = 0; i < ndev; i++) {
+        DevState& d = ctx->devs[i];
+        Shard& s = sh[i];
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(d.stream));
+        s.count = d.hs->count;
+        if (d.hs->overflow) {
+            s.cap = s.count;
+            if ((rc = d.pos.reserve(s.cap))) return rc;
+            if (p->want_sk && (rc = d.sk.reserve(s.cap))) return rc;
+            if (vw && (rc = d.val.reserve(s.cap * vw))) return rc;
+            const uint64_t blo = s.wb > 0 ? s.wb - 1 : 0;
+            const uint64_t byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
+            const uint64_t byte_hi = (bp_offset + s.we + l - 1 + 3) / 4;
+            mz::KArgs a{};
+            fill_hash_args(a, *p);
+            a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
+            a.bitbias = (int64_t)(2 * bp_offset) - (int64_t)(8 * byte_lo);
+            a.seq_nwords = (byte_hi - byte_lo + 3) / 4;
+            a.nwin = nwin;
+            a.pos = d.pos.p;
+            a.sk = d.sk.p;
+            a.val = d.val.p;
+            a.cap = s.cap;
+            if ((rc = enqueue_run(d, *p, a, s.wb, s.we, &ctx->timing.kernel_launches))) return rc;
+            CK(cudaEventRecord(d.ev[2], d.stream));
+            CK(cudaStreamSynchronize(d.stream));
+            if (d.hs->overflow) return MZ_ERR_CUDA;
+            s.count = d.hs->count;
+        }
+        total += s.count;
+    }
+    out->count = total;
+    if (total > out->capacity) return MZ_ERR_CAPACITY;
+    // phase 3: ordered gather into the caller's arrays
+    uint64_t off = 0;
+    for (size_t i = 0; i < ndev; i++) {
+        DevState& d = ctx->devs[i];
+        Shard& s = sh[i];
+        CK(cudaSetDevice(d.device));
+        if (s.count) {
+            CK(cudaMemcpyAsync(out->pos + off, d.pos.p, s.count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (p->want_sk) CK(cudaMemcpyAsync(out->sk + off, d.sk.p, s.count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (vw) CK(cudaMemcpyAsync(out->val + off * vw, d.val.p, s.count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+        }
+        CK(cudaEventRecord(d.ev[3], d.stream));
+        off += s.count;
+    }
+    for (size_t i = 0; i < ndev; i++) {
+        DevState& d = ctx->devs[i];
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(d.stream));
+        float h2d = 0, ker = 0, d2h = 0, tot = 0;
+        cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
+        cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
+        cudaEventElapsedTime(&d2h, d.ev[2], d.ev[3]);
+        cudaEventElapsedTime(&tot, d.ev[0], d.ev[3]);
+        ctx->timing.h2d_ms = std::max(ctx->timing.h2d_ms, h2d);
+        ctx->timing.kernel_ms = std::max(ctx->timing.kernel_ms, ker);
+        ctx->timing.d2h_ms = std::max(ctx->timing.d2h_ms, d2h);
+        ctx->timing.total_ms = std::max(ctx->timing.total_ms, tot);
+    }
+    return MZ_OK;
+}
+
+int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t packed_bytes,
+                 uint64_t n_reads, const uint64_t* read_start_bp, const uint32_t* read_len_bp,
+                 uint64_t stride_bytes, uint32_t fixed_len_bp, uint64_t* out_offsets, mz_out* out) {
+    (void)ctx, (void)p, (void)packed, (void)packed_bytes, (void)n_reads, (void)read_start_bp;
+    (void)read_len_bp, (void)stride_bytes, (void)fixed_len_bp, (void)out_offsets, (void)out;
+    return MZ_ERR_UNSUPPORTED;  // TODO(batch)
+}
+
+}  // extern "C"

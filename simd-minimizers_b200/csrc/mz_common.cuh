@@ -1,0 +1,235 @@
+// mz_common.cuh -- shared device helpers for the minimizer kernels (sm_100a).
+//
+// Semantics follow rust-seq/simd-minimizers v3.0.0 (citations relative to the reference tree):
+//   key = hash >> 16, leftmost / rightmost argmin   src/sliding_min.rs:102-105,126-129,190-195
+//   strand rule 2*#TG > l                           src/canonical.rs:19-29
+//   dedup + super-k-mer index                       src/collect.rs:39-76
+//   syncmer predicates                              src/syncmers.rs:33-37
+//   k-mer values                                    src/lib.rs:598-629
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mz {
+
+enum : uint32_t { MODE_MINIMIZER = 0, MODE_CLOSED = 1, MODE_OPEN = 2 };
+
+// Kernel arguments (POD, passed by value).
+struct KArgs {
+    const uint32_t* seq;  // packed 2-bit bases as 32-bit words (16 bases per word)
+    uint64_t seq_nwords;  // words readable at seq (loads are clamped to this)
+    int64_t bitbias;      // bit position of global base g inside seq = 2*g + bitbias
+    uint64_t nwin;        // windows of the whole sequence: n - l + 1
+    uint64_t wbeg, wend;  // window range produced by this launch
+    uint32_t k, w, l;
+    uint32_t S;           // windows per thread
+    uint32_t mode, want_sk, value_bits, val_len;
+    uint32_t val_canonical;  // values are min(kmer, revcomp) (Builder CANONICAL, src/lib.rs:602)
+    uint32_t f[4], c[4], rot;
+    uint32_t* pos;
+    uint32_t* sk;
+    uint64_t* val;
+    uint64_t cap;
+    unsigned long long* tile_state;  // decoupled look-back descriptors, zeroed before launch
+    uint32_t* ticket;                // dynamic tile id counter, zeroed before launch
+    unsigned long long* count_out;   // total entries produced by this launch
+    uint32_t* overflow;              // set to 1 when cap was too small
+    uint32_t num_tiles;
+    // batch mode (thread per read); reads == 0 -> single sequence
+    uint64_t n_reads;
+    const uint64_t* read_start_bp;   // may be null -> fixed stride
+    const uint32_t* read_len_bp;
+    uint64_t stride_bits;            // fixed stride between reads, in bits
+    uint32_t fixed_len_bp;
+    uint64_t* out_offsets;           // CSR offsets, n_reads + 1
+};
+
+__device__ __forceinline__ uint32_t rotl32(uint32_t x, uint32_t r) {
+    return __funnelshift_l(x, x, r);
+}
+__device__ __forceinline__ uint32_t rotr32(uint32_t x, uint32_t r) {
+    return __funnelshift_r(x, x, r);
+}
+
+__device__ __forceinline__ uint32_t ld_word(const KArgs& a, uint64_t widx) {
+    // clamp: bases past the end only ever feed windows that are discarded
+    widx = widx < a.seq_nwords ? widx : a.seq_nwords - 1;
+    return __ldg(a.seq + widx);
+}
+
+// 32 bits of the packed stream starting at absolute bit position `bit`
+__device__ __forceinline__ uint32_t ld_bits32(const KArgs& a, uint64_t bit) {
+    uint64_t wi = bit >> 5;
+    uint32_t sh = (uint32_t)bit & 31u;
+    uint32_t lo = ld_word(a, wi), hi = ld_word(a, wi + 1);
+    return __funnelshift_r(lo, hi, sh);
+}
+
+// Sequential reader of 2-bit bases from a bit position.
+struct BaseReader {
+    uint64_t widx;
+    uint32_t cur;
+    int left;
+    __device__ __forceinline__ void init(const KArgs& a, uint64_t bit) {
+        widx = bit >> 5;
+        uint32_t sh = (uint32_t)bit & 31u;
+        cur = ld_word(a, widx) >> sh;
+        left = (int)((32u - sh) >> 1);
+    }
+    __device__ __forceinline__ uint32_t next(const KArgs& a) {
+        if (left == 0) {
+            widx++;
+            cur = ld_word(a, widx);
+            left = 16;
+        }
+        uint32_t b = cur & 3u;
+        cur >>= 2;
+        left--;
+        return b;
+    }
+};
+
+// number of T/G bases (code & 2) among `len` bases starting at bit position `bit`
+__device__ __forceinline__ uint32_t tg_count(const KArgs& a, uint64_t bit, uint32_t len) {
+    uint32_t cnt = 0;
+    uint32_t bits = 2 * len;
+    while (bits >= 32) {
+        cnt += __popc(ld_bits32(a, bit) & 0xAAAAAAAAu);
+        bit += 32;
+        bits -= 32;
+    }
+    if (bits) cnt += __popc(ld_bits32(a, bit) & 0xAAAAAAAAu & ((1u << bits) - 1u));
+    return cnt;
+}
+
+__device__ __forceinline__ uint64_t swap_pairs64(uint64_t r) {
+    return ((r >> 1) & 0x5555555555555555ull) | ((r & 0x5555555555555555ull) << 1);
+}
+
+// 2-bit packed k-mer of `len` <= 32 bases at bit position `bit`; canonical: min(kmer, revcomp)
+__device__ __forceinline__ uint64_t kmer_value_u64(const KArgs& a, uint64_t bit, uint32_t len,
+                                                   bool canonical) {
+    uint64_t wi = bit >> 5;
+    uint32_t sh = (uint32_t)bit & 31u;
+    uint32_t w0 = ld_word(a, wi), w1 = ld_word(a, wi + 1), w2 = ld_word(a, wi + 2);
+    uint64_t v = (uint64_t)__funnelshift_r(w0, w1, sh) | ((uint64_t)__funnelshift_r(w1, w2, sh) << 32);
+    if (len < 32) v &= (1ull << (2 * len)) - 1ull;
+    if (!canonical) return v;
+    uint64_t r = swap_pairs64(__brevll(v)) ^ 0xAAAAAAAAAAAAAAAAull;
+    r >>= (64 - 2 * len);
+    return r < v ? r : v;
+}
+
+// len <= 64; result as (lo, hi)
+__device__ __forceinline__ void kmer_value_u128(const KArgs& a, uint64_t bit, uint32_t len,
+                                                bool canonical, uint64_t& lo, uint64_t& hi) {
+    uint64_t wi = bit >> 5;
+    uint32_t sh = (uint32_t)bit & 31u;
+    uint32_t w[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) w[i] = ld_word(a, wi + i);
+    uint64_t vlo = (uint64_t)__funnelshift_r(w[0], w[1], sh) | ((uint64_t)__funnelshift_r(w[1], w[2], sh) << 32);
+    uint64_t vhi = (uint64_t)__funnelshift_r(w[2], w[3], sh) | ((uint64_t)__funnelshift_r(w[3], w[4], sh) << 32);
+    if (len <= 32) {
+        vhi = 0;
+        if (len < 32) vlo &= (1ull << (2 * len)) - 1ull;
+    } else if (len < 64) {
+        vhi &= (1ull << (2 * (len - 32))) - 1ull;
+    }
+    lo = vlo;
+    hi = vhi;
+    if (!canonical) return;
+    // reverse the 128-bit value 2 bits at a time, complement, shift down by 128 - 2*len
+    uint64_t rhi = swap_pairs64(__brevll(vlo)) ^ 0xAAAAAAAAAAAAAAAAull;
+    uint64_t rlo = swap_pairs64(__brevll(vhi)) ^ 0xAAAAAAAAAAAAAAAAull;
+    uint32_t s = 128 - 2 * len;  // 0..126, even
+    uint64_t olo, ohi;
+    if (s == 0) {
+        olo = rlo, ohi = rhi;
+    } else if (s < 64) {
+        olo = (rlo >> s) | (rhi << (64 - s));
+        ohi = rhi >> s;
+    } else {
+        olo = rhi >> (s - 64);  // s == 64 -> shift 0
+        ohi = 0;
+    }
+    bool rc_smaller = (ohi < vhi) || (ohi == vhi && olo < vlo);
+    if (rc_smaller) lo = olo, hi = ohi;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decoupled look-back over tile descriptors: state = (value << 2) | status,
+// status 0 = not ready, 1 = tile aggregate, 2 = inclusive prefix.  Called by warp 0 of a block.
+// Returns the exclusive prefix of `tile` (sum of totals of all earlier tiles).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long ld_state(unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_state(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ unsigned long long lookback_warp0(unsigned long long* state,
+                                                              uint32_t tile,
+                                                              unsigned long long total) {
+    const uint32_t lane = threadIdx.x & 31u;
+    if (tile == 0) {
+        if (lane == 0) st_state(state, (total << 2) | 2ull);
+        return 0;
+    }
+    if (lane == 0) st_state(state + tile, (total << 2) | 1ull);
+    unsigned long long excl = 0;
+    int64_t base = (int64_t)tile - 1;
+    while (true) {
+        int64_t idx = base - (int64_t)lane;
+        unsigned long long v = 2ull;  // virtual tile before 0: inclusive prefix 0
+        if (idx >= 0) {
+            do {
+                v = ld_state(state + idx);
+            } while ((v & 3ull) == 0ull);
+        }
+        uint32_t is_prefix = __ballot_sync(0xffffffffu, (v & 3ull) == 2ull);
+        uint32_t first = is_prefix ? (uint32_t)__ffs(is_prefix) - 1u : 32u;
+        unsigned long long contrib = (lane <= first) ? (v >> 2) : 0ull;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+        excl += contrib;
+        if (is_prefix) break;
+        base -= 32;
+    }
+    if (lane == 0) st_state(state + tile, ((excl + total) << 2) | 2ull);
+    return excl;
+}
+
+// Block-wide exclusive scan of one uint32 per thread; returns exclusive prefix, sets total.
+// `scratch` needs blockDim.x/32 + 1 words of shared memory.
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* scratch,
+                                                         uint32_t& total) {
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= (uint32_t)o) inc += t;
+    }
+    if (lane == 31) scratch[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t x = lane < nwarps ? scratch[lane] : 0u;
+        uint32_t xi = x;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, xi, o);
+            if (lane >= (uint32_t)o) xi += t;
+        }
+        if (lane < nwarps) scratch[lane] = xi - x;
+        if (lane == 31) scratch[32] = xi;
+    }
+    __syncthreads();
+    total = scratch[32];
+    return scratch[warp] + inc - v;
+}
+
+}  // namespace mz

@@ -1,0 +1,251 @@
+// mz_generic.cuh -- runtime-(k,w) minimizer / syncmer kernel: any k, any w that fits the
+// shared-memory ring.  One thread walks S consecutive windows of the sequence (or one read in
+// batch mode) with a register-resident rolling hash and a two-stacks sliding minimum whose
+// ring lives in shared memory; results are recorded per window and emitted in a second,
+// ordered phase (block scan + decoupled look-back).  The W-specialised fast kernel
+// (mz_fast.cuh) shares phase 2 with this one.
+#pragma once
+#include "mz_common.cuh"
+
+namespace mz {
+
+// What one thread works on.
+struct Segment {
+    uint64_t bit0;      // bit position (in a.seq) of local base 0
+    uint64_t pos_base;  // added to a local k-mer index to give the output position
+    uint64_t win_base;  // window index reported for local valid window 0
+    uint32_t nvalid;    // windows this thread may emit
+    uint32_t has_prev;  // first computed window only seeds the dedup comparison
+    uint32_t first_always;
+    uint64_t read;      // batch mode: read index (else unused)
+};
+
+__device__ __forceinline__ Segment make_segment(const KArgs& a, uint32_t tile) {
+    Segment s;
+    const uint32_t NT = blockDim.x, tid = threadIdx.x;
+    if (a.n_reads == 0) {
+        uint64_t j0 = a.wbeg + ((uint64_t)tile * NT + tid) * a.S;
+        uint64_t left = j0 < a.wend ? a.wend - j0 : 0;
+        s.nvalid = (uint32_t)(left < a.S ? left : a.S);
+        s.has_prev = (j0 > 0 && a.mode == MODE_MINIMIZER) ? 1u : 0u;
+        uint64_t s0 = j0 - s.has_prev;
+        s.bit0 = (uint64_t)((int64_t)(2 * s0) + a.bitbias);
+        s.pos_base = s0;
+        s.win_base = j0;
+        s.first_always = (j0 == 0);
+        s.read = 0;
+    } else {
+        uint64_t r = (uint64_t)tile * NT + tid;
+        s.read = r;
+        s.has_prev = 0;
+        s.first_always = 1;
+        s.pos_base = 0;
+        s.win_base = 0;
+        s.nvalid = 0;
+        s.bit0 = 0;
+        if (r < a.n_reads) {
+            uint64_t startbits = a.read_start_bp ? 2 * a.read_start_bp[r] : r * a.stride_bits;
+            uint32_t len = a.read_len_bp ? a.read_len_bp[r] : a.fixed_len_bp;
+            s.bit0 = (uint64_t)((int64_t)startbits + a.bitbias);
+            s.nvalid = len >= a.l ? len - a.l + 1 : 0;
+        }
+    }
+    return s;
+}
+
+// -------------------------------------------------------------------------------------------
+// Phase 2 (shared): ordered emission.  rec(jv) returns the local selected k-mer index of valid
+// window jv; flag words hold `fbits` windows each, laid out flagw[q * NT + tid].
+// -------------------------------------------------------------------------------------------
+template <typename RecFn>
+__device__ __forceinline__ void emit_phase(const KArgs& a, const Segment& sg, uint32_t tile,
+                                           uint32_t cnt, const uint32_t* flagw, uint32_t fbits,
+                                           uint32_t* scratch, RecFn rec) {
+    const uint32_t NT = blockDim.x, tid = threadIdx.x;
+    __shared__ unsigned long long s_gbase;
+    uint32_t total;
+    uint32_t toff = block_exclusive_scan(cnt, scratch, total);
+    if (tid < 32) {
+        unsigned long long g = lookback_warp0(a.tile_state, tile, total);
+        if (tid == 0) {
+            s_gbase = g;
+            if (tile == a.num_tiles - 1) *a.count_out = g + total;
+        }
+    }
+    __syncthreads();
+    const unsigned long long gbase = s_gbase;
+    const bool ovf = gbase + total > a.cap;
+    if (ovf && tid == 0) *a.overflow = 1u;
+    if (a.n_reads != 0 && sg.read < a.n_reads) {
+        a.out_offsets[sg.read + 1] = gbase + toff + cnt;
+        if (sg.read == 0) a.out_offsets[0] = 0;
+    }
+    if (ovf || cnt == 0) return;
+
+    unsigned long long o = gbase + toff;
+    const bool minim = a.mode == MODE_MINIMIZER;
+    const bool canon_val = a.val_canonical != 0;
+    const uint32_t nq = (sg.nvalid + fbits - 1) / fbits;
+    for (uint32_t q = 0; q < nq; q++) {
+        uint32_t m = flagw[q * NT + tid];
+        while (m) {
+            uint32_t b = (uint32_t)__ffs(m) - 1u;
+            m &= m - 1u;
+            uint32_t jv = q * fbits + b;
+            uint32_t sel = rec(jv);
+            uint32_t local = minim ? sel : jv + sg.has_prev;  // local base index of the value
+            a.pos[o] = minim ? (uint32_t)(sg.pos_base + sel) : (uint32_t)(sg.win_base + jv);
+            if (a.want_sk) a.sk[o] = (uint32_t)(sg.win_base + jv);
+            if (a.value_bits == 64) {
+                a.val[o] = kmer_value_u64(a, sg.bit0 + 2ull * local, a.val_len, canon_val);
+            } else if (a.value_bits == 128) {
+                uint64_t lo, hi;
+                kmer_value_u128(a, sg.bit0 + 2ull * local, a.val_len, canon_val, lo, hi);
+                a.val[2 * o] = lo;
+                a.val[2 * o + 1] = hi;
+            }
+            o++;
+        }
+    }
+}
+
+// Dynamic shared memory layout of the generic kernel (NT = blockDim.x):
+//   uint2 tab[16]; uint32 misc[8]; uint32 scratch[40];
+//   uint32 flagw[ceil(S/32)][NT]; uint16 rec[S][NT]; ring[W][NT] (uint2 if LR else uint32)
+template <bool HC, bool LR>
+__global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t NT = blockDim.x, tid = threadIdx.x;
+    uint2* tab = reinterpret_cast<uint2*>(smem_raw);
+    uint32_t* misc = reinterpret_cast<uint32_t*>(tab + 16);
+    uint32_t* scratch = misc + 8;
+    uint32_t* flagw = scratch + 40;
+    const uint32_t nfw = (a.S + 31) / 32;
+    uint16_t* rec = reinterpret_cast<uint16_t*>(flagw + (size_t)nfw * NT);
+    // ring starts 8-byte aligned: S*NT*2 bytes with NT multiple of 32 is a multiple of 8
+    unsigned char* ring_raw = reinterpret_cast<unsigned char*>(rec + (size_t)a.S * NT);
+    uint2* ring2 = reinterpret_cast<uint2*>(ring_raw);
+    uint32_t* ring1 = reinterpret_cast<uint32_t*>(ring_raw);
+
+    const uint32_t k = a.k, w = a.w, l = a.l, R = a.rot;
+    if (tid < 16) {
+        uint32_t in = tid & 3u, out = tid >> 2;
+        // delta of one rolling step that adds base `in` and drops base `out` (k bases earlier)
+        uint32_t dfw = a.f[in] ^ rotl32(a.f[out], (R * k) & 31u);
+        uint32_t drc = rotl32(a.c[in], (R * (k - 1)) & 31u) ^ rotr32(a.c[out], R & 31u);
+        tab[tid] = make_uint2(dfw, drc);
+    }
+    if (tid == 0) {
+        misc[0] = atomicAdd(a.ticket, 1u);
+        // hash state of the virtual all-'A' k-mer that precedes every segment
+        uint32_t fa = 0, ca = 0;
+        for (uint32_t j = 0; j < k; j++) {
+            fa ^= rotl32(a.f[0], (R * j) & 31u);
+            ca ^= rotl32(a.c[0], (R * j) & 31u);
+        }
+        misc[1] = fa;
+        misc[2] = ca;
+    }
+    __syncthreads();
+    const uint32_t tile = misc[0];
+    const Segment sg = make_segment(a, tile);
+
+    uint32_t cnt = 0;
+    if (sg.nvalid) {
+        uint32_t fw = misc[1], rc = misc[2];
+        BaseReader in, out;
+        in.init(a, sg.bit0);
+        out.init(a, sg.bit0);
+        for (uint32_t s = 0; s < w; s++) {
+            if (LR) ring2[s * NT + tid] = make_uint2(0xffffffffu, 0u);
+            else ring1[s * NT + tid] = 0xffffffffu;
+        }
+        uint32_t slot = 0, preL = 0xffffffffu, preR = 0u;
+        uint32_t prev = 0xffffffffu, flags = 0;
+        const uint32_t nsteps = sg.nvalid + sg.has_prev + l - 1;
+        const uint32_t mode = a.mode;
+        for (uint32_t t = 0; t < nsteps; t++) {
+            uint32_t b_in = in.next(a);
+            uint32_t b_out = t >= k ? out.next(a) : 0u;
+            uint2 d = tab[b_in | (b_out << 2)];
+            fw = rotl32(fw, R) ^ d.x;
+            uint32_t h = fw;
+            if (HC) {
+                rc = rotr32(rc, R) ^ d.y;
+                h = fw + rc;
+            }
+            if (t + 1 < k) continue;
+            const uint32_t e = t - (k - 1);  // local k-mer index
+            const uint32_t le = (h & 0xffff0000u) | e;
+            const uint32_t re = (~h & 0xffff0000u) | e;
+            uint32_t sufL, sufR = 0;
+            if (LR) {
+                ring2[slot * NT + tid] = make_uint2(le, re);
+                preL = min(preL, le);
+                preR = max(preR, re);
+                if (++slot == w) {
+                    slot = 0;
+                    uint2 sfx = ring2[(w - 1) * NT + tid];
+                    for (uint32_t q = w - 1; q-- > 0;) {
+                        uint2 x = ring2[q * NT + tid];
+                        sfx.x = min(sfx.x, x.x);
+                        sfx.y = max(sfx.y, x.y);
+                        ring2[q * NT + tid] = sfx;
+                    }
+                    preL = le;
+                    preR = re;
+                }
+                uint2 sf = ring2[slot * NT + tid];
+                sufL = sf.x;
+                sufR = sf.y;
+            } else {
+                ring1[slot * NT + tid] = le;
+                preL = min(preL, le);
+                if (++slot == w) {
+                    slot = 0;
+                    uint32_t sfx = ring1[(w - 1) * NT + tid];
+                    for (uint32_t q = w - 1; q-- > 0;) {
+                        sfx = min(sfx, ring1[q * NT + tid]);
+                        ring1[q * NT + tid] = sfx;
+                    }
+                    preL = le;
+                }
+                sufL = ring1[slot * NT + tid];
+            }
+            if (e + 1 < w) continue;
+            const uint32_t jl = e - (w - 1);  // local window index
+            uint32_t sel = min(preL, sufL) & 0xffffu;
+            if (LR) {
+                uint32_t selR = max(preR, sufR) & 0xffffu;
+                if (sel != selR) {
+                    // strand rule, evaluated only when leftmost != rightmost
+                    uint32_t tg = tg_count(a, sg.bit0 + 2ull * jl, l);
+                    if (!(2 * tg > l)) sel = selR;
+                }
+            }
+            const int jv = (int)jl - (int)sg.has_prev;
+            bool flag;
+            if (mode == MODE_MINIMIZER) flag = (jv == 0 && sg.first_always) || sel != prev;
+            else if (mode == MODE_CLOSED) flag = sel == jl || sel == jl + w - 1;
+            else flag = sel == jl + w / 2;
+            prev = sel;
+            if (jv >= 0) {
+                rec[(uint32_t)jv * NT + tid] = (uint16_t)sel;
+                if (flag) flags |= 1u << (jv & 31);
+                if ((jv & 31) == 31) {
+                    flagw[((uint32_t)jv >> 5) * NT + tid] = flags;
+                    cnt += __popc(flags);
+                    flags = 0;
+                }
+            }
+        }
+        if (sg.nvalid & 31u) {
+            flagw[(sg.nvalid >> 5) * NT + tid] = flags;
+            cnt += __popc(flags);
+        }
+    }
+    emit_phase(a, sg, tile, cnt, flagw, 32u, scratch,
+               [&](uint32_t jv) -> uint32_t { return rec[jv * NT + tid]; });
+}
+
+}  // namespace mz

@@ -1,0 +1,230 @@
+"""GPU parity tests (run with -m gpu on a B200): the CUDA path, called through the C ABI,
+against the CPU oracle -- bit-exact positions, super-k-mer starts, values and syncmers on the
+reference's (k, w, len, offset) grid (src/test.rs:24-51), the reference's golden vectors, and
+size-independent properties at larger sizes."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "reference_vectors.json")
+KS = [1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65]
+WS = [1, 2, 3, 4, 5, 31, 32, 33, 63, 64, 65]
+
+
+def _builder(sm, k, w, canonical, mode):
+    f = {(False, 0): sm.minimizers, (True, 0): sm.canonical_minimizers,
+         (False, 1): sm.closed_syncmers, (True, 1): sm.canonical_closed_syncmers,
+         (False, 2): sm.open_syncmers, (True, 2): sm.canonical_open_syncmers}[(canonical, mode)]
+    return f(k, w)
+
+
+def _check_case(sm, oracle, packed, off, n, k, w, canonical, mode, kind="nt", hash_canon=None):
+    if hash_canon is None:
+        hash_canon = canonical
+    seq = sm.PackedSeq(packed, off, n)
+    b = _builder(sm, k, w, canonical, mode)
+    if kind != "nt" or hash_canon != canonical:
+        H = sm.NtHasher if kind == "nt" else sm.MulHasher
+        b = b.hasher(H(k, hash_canon))
+    pr = oracle.make_params(k, w, canonical=canonical, mode=mode,
+                            hasher=oracle.make_hasher(kind, hash_canon))
+    epos, esk = oracle.run(packed, off, n, pr, "stream", want_sk=(mode == 0))
+    pos, sk = sm.U32Vec(), sm.U32Vec()
+    out = (b.super_kmers(sk) if mode == 0 else b).run(seq, pos)
+    tag = (k, w, n, off, canonical, mode, kind)
+    assert np.array_equal(pos.array, epos), tag
+    if mode == 0:
+        assert np.array_equal(sk.array, esk), tag
+    length = k if mode == 0 else k + w - 1
+    if length <= 32:
+        assert np.array_equal(out.values_u64(), oracle.values_u64(packed, off, length, canonical, epos)), tag
+    elif length <= 64:
+        got = out._values(128)
+        assert np.array_equal(got, oracle.values_u128(packed, off, length, canonical, epos)), tag
+
+
+def test_reference_golden_vectors(sm):
+    v = json.load(open(GOLDEN))
+    d = v["doc_forward"]
+    s = sm.PackedSeqVec.from_ascii(d["seq"].encode())
+    assert sm.minimizer_positions(s, d["k"], d["w"]).tolist() == d["pos"]
+    d = v["doc_canonical"]
+    s = sm.PackedSeqVec.from_ascii(d["seq"].encode())
+    assert sm.canonical_minimizer_positions(s, d["k"], d["w"]).tolist() == d["pos"]
+    pos = sm.U32Vec()
+    vals = sm.canonical_minimizers(d["k"], d["w"]).run(s, pos).values_u64()
+    assert pos.tolist() == d["pos"] and vals.tolist() == d["values"]
+    rc = s.as_slice().to_revcomp()
+    rpos = sm.U32Vec()
+    rvals = sm.canonical_minimizers(d["k"], d["w"]).run(rc, rpos).values_u64()
+    assert rpos.tolist() == d["rc_pos"] and rvals.tolist()[::-1] == d["values"]
+
+
+def test_closed_syncmer_values_all_g(sm):
+    n = 100                                     # src/test.rs:578-597
+    s = sm.PackedSeqVec.from_ascii(b"G" * n)
+    for k in range(1, 10):
+        for w in range(1, 10):
+            pos = sm.U32Vec()
+            vals = sm.closed_syncmers(k, w).run(s, pos).values_u64()
+            assert len(vals) == n - (k + w - 1) + 1
+            assert (vals == (1 << (2 * (k + w - 1))) - 1).all()
+
+
+@pytest.mark.parametrize("canonical", [False, True])
+def test_minimizer_grid(sm, oracle, canonical):
+    """src/test.rs:55-110, 155-277 grid: every (k, w) pair, short + long lengths, offsets 0..3."""
+    rng = np.random.default_rng(11 + canonical)
+    base = oracle.synth_packed(99, 8192 + 8)
+    ks = KS + [int(x) for x in rng.integers(6, 100, 3)]
+    ws = WS + [int(x) for x in rng.integers(6, 100, 3)]
+    for k in ks:
+        for w in ws:
+            if canonical and (k + w - 1) % 2 == 0:
+                continue
+            lens = [int(x) for x in rng.integers(0, 100, 3)] + [k + w - 2, k + w - 1, k + w,
+                    int(rng.integers(100, 8192))]
+            for n in lens:
+                off = int(rng.integers(0, 4))
+                _check_case(sm, oracle, base, off, n, k, w, canonical, 0)
+
+
+def test_all_short_lengths(sm, oracle):
+    base = oracle.synth_packed(5, 128)
+    for n in range(0, 100):
+        for (k, w, c) in ((5, 7, True), (3, 4, False), (31, 19, True), (1, 1, True)):
+            _check_case(sm, oracle, base, n % 4, n, k, w, c, 0)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_syncmer_grid(sm, oracle, mode):
+    """src/test.rs:519-574, 600-639"""
+    rng = np.random.default_rng(100 + mode)
+    base = oracle.synth_packed(123, 8192 + 8)
+    for k in KS[:8] + [int(x) for x in rng.integers(6, 60, 2)]:
+        for w in WS[:8] + [int(x) for x in rng.integers(6, 60, 2)]:
+            if mode == 2 and w % 2 == 0:
+                continue
+            for canonical in (False, True):
+                if canonical and (k + w - 1) % 2 == 0:
+                    continue
+                for n in (int(rng.integers(0, 100)), int(rng.integers(100, 4096))):
+                    _check_case(sm, oracle, base, int(rng.integers(0, 4)), n, k, w, canonical, mode)
+
+
+def test_hashers(sm, oracle):
+    """MulHasher, and a forward builder with a canonical hasher (src/minimizers.rs:69-71)."""
+    rng = np.random.default_rng(5)
+    base = oracle.synth_packed(77, 6000)
+    for _ in range(40):
+        k, w = int(rng.integers(1, 50)), int(rng.integers(1, 40))
+        n, off = int(rng.integers(0, 5000)), int(rng.integers(0, 4))
+        _check_case(sm, oracle, base, off, n, k, w, False, 0, kind="mul")
+        _check_case(sm, oracle, base, off, n, k, w, False, 0, kind="nt", hash_canon=True)
+        if (k + w - 1) % 2 == 1:
+            _check_case(sm, oracle, base, off, n, k, w, True, 0, kind="mul")
+
+
+def test_degenerate_sequences(sm, oracle):
+    """Homopolymers / short periods: every window emits (density 1) or ties everywhere."""
+    for pattern in (b"A", b"G", b"AC", b"ACGT", b"AAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAAT"):
+        s = (pattern * (3000 // len(pattern) + 1))[:3000]
+        packed = oracle.pack_ascii(s)
+        for (k, w, c) in ((31, 19, True), (21, 11, False), (5, 3, True), (8, 1, False)):
+            for mode in (0, 1):
+                _check_case(sm, oracle, packed, 0, len(s), k, w, c, mode)
+
+
+def test_error_behaviour(sm):
+    s = sm.PackedSeqVec.random(200, 1)
+    with pytest.raises(AssertionError, match="must be odd"):
+        sm.canonical_minimizer_positions(s, 4, 3)
+    with pytest.raises(AssertionError, match="Open syncmers require odd"):
+        sm.open_syncmers(5, 4).run_once(s)
+    with pytest.raises(AssertionError):
+        sm.canonical_minimizers(5, 7).hasher(sm.NtHasher(5, False)).run_once(s)
+    pos = sm.U32Vec()
+    out = sm.canonical_minimizers(33, 3).run(s, pos)
+    with pytest.raises(AssertionError):
+        out.values_u64()
+    assert len(out.values_u128()) == len(pos)
+
+
+def test_append_semantics(sm, oracle):
+    """Positions are appended; the first new element is dropped if it repeats the last one
+    (src/collect.rs:257,267)."""
+    s = sm.PackedSeqVec.random(500, 3)
+    first = sm.minimizer_positions(s, 7, 5)
+    v = sm.U32Vec()
+    sm.minimizers(7, 5).run(s, v)
+    sm.minimizers(7, 5).run(s, v)
+    assert v.tolist() == first.tolist() + first.tolist()
+    v = sm.U32Vec([int(first[0])])
+    sm.minimizers(7, 5).run(s, v)
+    assert v.tolist() == first.tolist()
+
+
+def test_medium_exact_and_rc_symmetry(sm, oracle):
+    """10 Mbp (BASELINE config 1 size) exact compare, plus rc symmetry at the same size."""
+    n = 10_000_000
+    packed = oracle.synth_packed(42, n)
+    for (k, w, c) in ((21, 11, False), (31, 19, True)):
+        _check_case(sm, oracle, packed, 0, n, k, w, c, 0)
+    seq = sm.PackedSeq(packed, 0, n)
+    rc = sm.PackedSeq(oracle.revcomp(packed, 0, n), 0, n)
+    fpos, rpos = sm.U32Vec(), sm.U32Vec()
+    fv = sm.canonical_minimizers(31, 19).run(seq, fpos).values_u64()
+    rv = sm.canonical_minimizers(31, 19).run(rc, rpos).values_u64()
+    assert len(fpos) == len(rpos)
+    assert (fpos.array.astype(np.int64) + rpos.array[::-1].astype(np.int64) == n - 31).all()
+    assert np.array_equal(fv, rv[::-1])
+
+
+def test_device_resident_and_window_ranges(sm, oracle):
+    """mz_run_device: device pointers in/out, arbitrary window sub-ranges concatenate to the
+    full result (the multi-GPU shard rule)."""
+    import ctypes as C
+    import importlib
+
+    import torch
+
+    ffi = importlib.import_module("simd-minimizers_b200._ffi")
+    L = ffi.lib()
+    n, k, w = 300_000, 31, 19
+    packed = oracle.synth_packed(9, n + 1)
+    pr = oracle.make_params(k, w, canonical=True)
+    epos, esk = oracle.run(packed, 1, n, pr, want_sk=True)
+    evals = oracle.values_u64(packed, 1, k, True, epos)
+    d_in = torch.from_numpy(packed).cuda()
+    ctx = sm.Context()
+    p = ffi.MzParams()
+    L.mz_params_nthash(C.byref(p), k, w, 0, 1)
+    p.want_sk, p.value_bits = 1, 64
+    nwin = n - (k + w - 1) + 1
+    cuts = [0, 1, 77, 4096, 150_001, nwin]
+    got_p, got_s, got_v = [], [], []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        cap = b - a
+        dp = torch.empty(cap, dtype=torch.int32, device="cuda")
+        ds = torch.empty(cap, dtype=torch.int32, device="cuda")
+        dv = torch.empty(cap, dtype=torch.int64, device="cuda")
+        out = ffi.MzOut(dp.data_ptr(), ds.data_ptr(), dv.data_ptr(), cap, 0)
+        rc = L.mz_run_device(ctx.handle, 0, C.byref(p), d_in.data_ptr(), 1, n, a, b, C.byref(out))
+        assert rc == 0
+        m = out.count
+        got_p.append(dp[:m].cpu().numpy().view(np.uint32))
+        got_s.append(ds[:m].cpu().numpy().view(np.uint32))
+        got_v.append(dv[:m].cpu().numpy().view(np.uint64))
+    assert np.array_equal(np.concatenate(got_p), epos)
+    assert np.array_equal(np.concatenate(got_s), esk)
+    assert np.array_equal(np.concatenate(got_v), evals)
+    # capacity too small -> MZ_ERR_CAPACITY with the needed count
+    dp = torch.empty(10, dtype=torch.int32, device="cuda")
+    out = ffi.MzOut(dp.data_ptr(), dp.data_ptr(), dp.data_ptr(), 10, 0)
+    p.want_sk, p.value_bits = 0, 0
+    rc = L.mz_run_device(ctx.handle, 0, C.byref(p), d_in.data_ptr(), 1, n, 0, 0, C.byref(out))
+    assert rc == 8 and out.count == len(epos)
