@@ -59,8 +59,8 @@ struct DevBuf {
 
 struct HostScalars {  // pinned
     unsigned long long count;
+    uint32_t ticket;
     uint32_t overflow;
-    uint32_t pad;
 };
 
 struct DevState {
@@ -502,7 +502,10 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
             if ((rc = enqueue_run(d, *p, a, s.wb, s.we, &ctx->timing.kernel_launches))) return rc;
             CK(cudaEventRecord(d.ev[2], d.stream));
             CK(cudaStreamSynchronize(d.stream));
-            if (d.hs->overflow) return MZ_ERR_CUDA;
+            if (d.hs->overflow) {
+                g_last_error = "internal: exact-capacity re-run overflowed";
+                return MZ_ERR_CUDA;
+            }
             s.count = d.hs->count;
         }
         total += s.count;
