@@ -98,7 +98,7 @@ struct Plan {
 uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
 
 size_t generic_smem(uint32_t NT, uint32_t S, uint32_t w, bool lr) {
-    size_t fixed = 16 * 8 + 8 * 4 + 40 * 4;
+    size_t fixed = 16 * 8 + 8 * 4 + mz::EMIT_SMEM_BYTES;
     size_t per_thread = (size_t)((S + 31) / 32) * 4 + (size_t)S * 2 + (size_t)w * (lr ? 8 : 4);
     return fixed + per_thread * NT;
 }

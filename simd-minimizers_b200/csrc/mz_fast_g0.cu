@@ -1,0 +1,19 @@
+// Instantiations of the W-specialised kernel for W = 1 .. 8 (split across translation
+// units so the build parallelises).
+#include "mz_fast.cuh"
+namespace mz {
+int launch_fast_g0(const mz_params& p, uint32_t NT, size_t smem, uint32_t tiles, const KArgs& a,
+                    cudaStream_t st) {
+    switch (p.w) {
+        case 1: return launch_fast_w<1>(p, NT, smem, tiles, a, st);
+        case 2: return launch_fast_w<2>(p, NT, smem, tiles, a, st);
+        case 3: return launch_fast_w<3>(p, NT, smem, tiles, a, st);
+        case 4: return launch_fast_w<4>(p, NT, smem, tiles, a, st);
+        case 5: return launch_fast_w<5>(p, NT, smem, tiles, a, st);
+        case 6: return launch_fast_w<6>(p, NT, smem, tiles, a, st);
+        case 7: return launch_fast_w<7>(p, NT, smem, tiles, a, st);
+        case 8: return launch_fast_w<8>(p, NT, smem, tiles, a, st);
+        default: return MZ_ERR_UNSUPPORTED;
+    }
+}
+}  // namespace mz

@@ -5,112 +5,12 @@
 // ordered phase (block scan + decoupled look-back).  The W-specialised fast kernel
 // (mz_fast.cuh) shares phase 2 with this one.
 #pragma once
-#include "mz_common.cuh"
+#include "mz_emit.cuh"
 
 namespace mz {
 
-// What one thread works on.
-struct Segment {
-    uint64_t bit0;      // bit position (in a.seq) of local base 0
-    uint64_t pos_base;  // added to a local k-mer index to give the output position
-    uint64_t win_base;  // window index reported for local valid window 0
-    uint32_t nvalid;    // windows this thread may emit
-    uint32_t has_prev;  // first computed window only seeds the dedup comparison
-    uint32_t first_always;
-    uint64_t read;      // batch mode: read index (else unused)
-};
-
-__device__ __forceinline__ Segment make_segment(const KArgs& a, uint32_t tile) {
-    Segment s;
-    const uint32_t NT = blockDim.x, tid = threadIdx.x;
-    if (a.n_reads == 0) {
-        uint64_t j0 = a.wbeg + ((uint64_t)tile * NT + tid) * a.S;
-        uint64_t left = j0 < a.wend ? a.wend - j0 : 0;
-        s.nvalid = (uint32_t)(left < a.S ? left : a.S);
-        s.has_prev = (j0 > 0 && a.mode == MODE_MINIMIZER) ? 1u : 0u;
-        uint64_t s0 = j0 - s.has_prev;
-        s.bit0 = (uint64_t)((int64_t)(2 * s0) + a.bitbias);
-        s.pos_base = s0;
-        s.win_base = j0;
-        s.first_always = (j0 == 0);
-        s.read = 0;
-    } else {
-        uint64_t r = (uint64_t)tile * NT + tid;
-        s.read = r;
-        s.has_prev = 0;
-        s.first_always = 1;
-        s.pos_base = 0;
-        s.win_base = 0;
-        s.nvalid = 0;
-        s.bit0 = 0;
-        if (r < a.n_reads) {
-            uint64_t startbits = a.read_start_bp ? 2 * a.read_start_bp[r] : r * a.stride_bits;
-            uint32_t len = a.read_len_bp ? a.read_len_bp[r] : a.fixed_len_bp;
-            s.bit0 = (uint64_t)((int64_t)startbits + a.bitbias);
-            s.nvalid = len >= a.l ? len - a.l + 1 : 0;
-        }
-    }
-    return s;
-}
-
-// -------------------------------------------------------------------------------------------
-// Phase 2 (shared): ordered emission.  rec(jv) returns the local selected k-mer index of valid
-// window jv; flag words hold `fbits` windows each, laid out flagw[q * NT + tid].
-// -------------------------------------------------------------------------------------------
-template <typename RecFn>
-__device__ __forceinline__ void emit_phase(const KArgs& a, const Segment& sg, uint32_t tile,
-                                           uint32_t cnt, const uint32_t* flagw, uint32_t fbits,
-                                           uint32_t* scratch, RecFn rec) {
-    const uint32_t NT = blockDim.x, tid = threadIdx.x;
-    __shared__ unsigned long long s_gbase;
-    uint32_t total;
-    uint32_t toff = block_exclusive_scan(cnt, scratch, total);
-    if (tid < 32) {
-        unsigned long long g = lookback_warp0(a.tile_state, tile, total);
-        if (tid == 0) {
-            s_gbase = g;
-            if (tile == a.num_tiles - 1) *a.count_out = g + total;
-        }
-    }
-    __syncthreads();
-    const unsigned long long gbase = s_gbase;
-    const bool ovf = gbase + total > a.cap;
-    if (ovf && tid == 0) *a.overflow = 1u;
-    if (a.n_reads != 0 && sg.read < a.n_reads) {
-        a.out_offsets[sg.read + 1] = gbase + toff + cnt;
-        if (sg.read == 0) a.out_offsets[0] = 0;
-    }
-    if (ovf || cnt == 0) return;
-
-    unsigned long long o = gbase + toff;
-    const bool minim = a.mode == MODE_MINIMIZER;
-    const bool canon_val = a.val_canonical != 0;
-    const uint32_t nq = (sg.nvalid + fbits - 1) / fbits;
-    for (uint32_t q = 0; q < nq; q++) {
-        uint32_t m = flagw[q * NT + tid];
-        while (m) {
-            uint32_t b = (uint32_t)__ffs(m) - 1u;
-            m &= m - 1u;
-            uint32_t jv = q * fbits + b;
-            uint32_t sel = rec(jv);
-            uint32_t local = minim ? sel : jv + sg.has_prev;  // local base index of the value
-            a.pos[o] = minim ? (uint32_t)(sg.pos_base + sel) : (uint32_t)(sg.win_base + jv);
-            if (a.want_sk) a.sk[o] = (uint32_t)(sg.win_base + jv);
-            if (a.value_bits == 64) {
-                a.val[o] = kmer_value_u64(a, sg.bit0 + 2ull * local, a.val_len, canon_val);
-            } else if (a.value_bits == 128) {
-                uint64_t lo, hi;
-                kmer_value_u128(a, sg.bit0 + 2ull * local, a.val_len, canon_val, lo, hi);
-                a.val[2 * o] = lo;
-                a.val[2 * o + 1] = hi;
-            }
-            o++;
-        }
-    }
-}
-
 // Dynamic shared memory layout of the generic kernel (NT = blockDim.x):
-//   uint2 tab[16]; uint32 misc[8]; uint32 scratch[40];
+//   uint2 tab[16]; uint32 misc[8]; emit staging (EMIT_SMEM_BYTES);
 //   uint32 flagw[ceil(S/32)][NT]; uint16 rec[S][NT]; ring[W][NT] (uint2 if LR else uint32)
 template <bool HC, bool LR>
 __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
@@ -118,8 +18,8 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
     const uint32_t NT = blockDim.x, tid = threadIdx.x;
     uint2* tab = reinterpret_cast<uint2*>(smem_raw);
     uint32_t* misc = reinterpret_cast<uint32_t*>(tab + 16);
-    uint32_t* scratch = misc + 8;
-    uint32_t* flagw = scratch + 40;
+    const EmitSmem es = EmitSmem::carve(reinterpret_cast<unsigned char*>(misc + 8));
+    uint32_t* flagw = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(misc + 8) + EMIT_SMEM_BYTES);
     const uint32_t nfw = (a.S + 31) / 32;
     uint16_t* rec = reinterpret_cast<uint16_t*>(flagw + (size_t)nfw * NT);
     // ring starts 8-byte aligned: S*NT*2 bytes with NT multiple of 32 is a multiple of 8
@@ -148,7 +48,7 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
     }
     __syncthreads();
     const uint32_t tile = misc[0];
-    const Segment sg = make_segment(a, tile);
+    const Segment sg = make_segment(a, tile, tid);
 
     uint32_t cnt = 0;
     if (sg.nvalid) {
@@ -244,8 +144,11 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
             cnt += __popc(flags);
         }
     }
-    emit_phase(a, sg, tile, cnt, flagw, 32u, scratch,
-               [&](uint32_t jv) -> uint32_t { return rec[jv * NT + tid]; });
+    emit_phase(a, sg, tile, cnt, flagw, (sg.nvalid + 31u) / 32u, es,
+               [&](uint32_t q, uint32_t bit, uint32_t& jv, uint32_t& d) {
+                   jv = q * 32u + bit;
+                   d = (uint32_t)rec[jv * NT + tid] - (jv + sg.has_prev);
+               });
 }
 
 }  // namespace mz
