@@ -70,6 +70,7 @@ struct DevState {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> scratch;  // [0]=count [1]=ticket|overflow [2..]=tile_state
+    DevBuf<uint32_t> rows;               // fast kernel per-block record rows
     DevBuf<uint8_t> in;
     DevBuf<uint32_t> pos, sk;
     DevBuf<uint64_t> val;
@@ -170,10 +171,18 @@ int launch_generic(const mz_params& p, const Plan& pl, const mz::KArgs& a, cudaS
 int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uint64_t wend,
                 uint32_t* launches) {
     Plan pl;
-    int rc = mz::plan_fast(d.sm_count, d.smem_optin, p, wend - wbeg, &pl.NT, &pl.S, &pl.smem,
-                           &pl.num_tiles)
-                 ? (pl.fast = true, MZ_OK)
-                 : plan_generic(d, p, wend - wbeg, &pl);
+    mz::FastPlan fp;
+    int rc = MZ_OK;
+    if (mz::plan_fast(d.sm_count, p, wend - wbeg, &fp)) {
+        pl.fast = true;
+        pl.S = fp.S;
+        pl.num_tiles = fp.num_tiles;
+        if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS))) return rc;
+        a.scratch = d.rows.p;
+        a.scratch_words_per_block = fp.scratch_words_per_block;
+    } else {
+        rc = plan_generic(d, p, wend - wbeg, &pl);
+    }
     if (rc) return rc;
     if ((rc = d.scratch.reserve(2 + (size_t)pl.num_tiles))) return rc;
     CK(cudaMemsetAsync(d.scratch.p, 0, (2 + (size_t)pl.num_tiles) * sizeof(unsigned long long), d.stream));
@@ -185,7 +194,7 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
     a.ticket = reinterpret_cast<uint32_t*>(d.scratch.p + 1);
     a.overflow = a.ticket + 1;
     a.tile_state = d.scratch.p + 2;
-    if (pl.fast) rc = mz::launch_fast(p, pl.NT, pl.smem, pl.num_tiles, a, d.stream);
+    if (pl.fast) rc = mz::launch_fast(p, fp.grid, a, d.stream);
     else rc = launch_generic(p, pl, a, d.stream);
     if (rc > 0 && rc != MZ_OK) {
         if (rc == MZ_ERR_CUDA && g_last_error.empty()) g_last_error = "kernel launch failed";
@@ -349,7 +358,7 @@ void mz_ctx_destroy(mz_ctx* ctx) {
     for (DevState& d : ctx->devs) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        d.scratch.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
+        d.scratch.release(), d.rows.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
         d.offs.release(), d.rstart.release(), d.rlen.release();
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);

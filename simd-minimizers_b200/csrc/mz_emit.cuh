@@ -23,9 +23,10 @@ struct Segment {
 // Segment of thread `tid` of tile `tile`.  Single sequence: S consecutive windows, plus one
 // window on the left whose result only seeds the dedup comparison (the reference's lane-seam
 // rule, src/collect.rs:252-272).  Batch mode: one read per thread.
-__device__ __forceinline__ Segment make_segment(const KArgs& a, uint32_t tile, uint32_t tid) {
+// NT = threads per tile.
+__device__ __forceinline__ Segment make_segment_nt(const KArgs& a, uint32_t tile, uint32_t tid,
+                                                   uint32_t NT) {
     Segment s;
-    const uint32_t NT = blockDim.x;
     if (a.n_reads == 0) {
         uint64_t j0 = a.wbeg + ((uint64_t)tile * NT + tid) * a.S;
         uint64_t left = j0 < a.wend ? a.wend - j0 : 0;
@@ -54,6 +55,10 @@ __device__ __forceinline__ Segment make_segment(const KArgs& a, uint32_t tile, u
     return s;
 }
 
+__device__ __forceinline__ Segment make_segment(const KArgs& a, uint32_t tile, uint32_t tid) {
+    return make_segment_nt(a, tile, tid, blockDim.x);
+}
+
 constexpr uint32_t EMIT_CHUNK = 2048;  // entries staged per round
 // shared memory used by emit_phase: scratch (40 words) + list_a (u32) + list_b (u16)
 constexpr uint32_t EMIT_SMEM_BYTES = 40 * 4 + EMIT_CHUNK * 4 + EMIT_CHUNK * 2;
@@ -71,12 +76,13 @@ struct EmitSmem {
     }
 };
 
+// Flag word q of a thread lives at flagw[q * fstride * NT + tid].
 // dec(q, bit, jv, d): decode bit `bit` of this thread's flag word q into the valid-window index
 // jv and d = (selected local k-mer index) - (local window index).
 template <typename DecFn>
 __device__ __forceinline__ void emit_phase(const KArgs& a, const Segment& sg, uint32_t tile,
-                                           uint32_t cnt, const uint32_t* flagw, uint32_t nq,
-                                           const EmitSmem& es, DecFn dec) {
+                                           uint32_t cnt, const uint32_t* flagw, uint32_t fstride,
+                                           uint32_t nq, const EmitSmem& es, DecFn dec) {
     const uint32_t NT = blockDim.x, tid = threadIdx.x;
     __shared__ unsigned long long s_gbase;
     uint32_t total;
@@ -110,7 +116,7 @@ __device__ __forceinline__ void emit_phase(const KArgs& a, const Segment& sg, ui
         while (produced < cnt && toff + produced < cbase + EMIT_CHUNK) {
             while (m == 0) {
                 q++;
-                m = flagw[q * NT + tid];
+                m = flagw[(size_t)q * fstride * NT + tid];
             }
             uint32_t bit = (uint32_t)__ffs(m) - 1u;
             m &= m - 1u;

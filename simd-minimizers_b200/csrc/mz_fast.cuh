@@ -1,17 +1,21 @@
 // mz_fast.cuh -- W-specialised, register-resident minimizer / syncmer kernel for sm_100a.
 //
+// Persistent warps pull tiles (32 threads x S windows) from a ticket counter; every warp is an
+// autonomous worker (own look-back, own staging), so there is no block barrier after start-up.
 // One thread walks S consecutive windows.  Per van-Herk block of W k-mers (fully unrolled):
-//   * 2W bits of the entering- and leaving-base streams are fetched and re-aligned with funnel
-//     shifts, then interleaved so that every byte holds (in,in,out,out) of two consecutive bases;
+//   * the words holding the entering- and leaving-base streams were prefetched one block ahead;
+//     they are re-aligned with funnel shifts and interleaved so that every byte holds
+//     (in,in,out,out) of two consecutive bases;
 //   * one LDS.128 from a 256-entry table returns the rolling-hash deltas of BOTH bases for the
 //     forward and the reverse-complement hash (ntHash/mulHash are GF(2)-linear in the tables),
 //     so a k-mer hash costs SHF+LOP3 per strand;
 //   * (hash & 0xffff0000) | pos goes through a prefix-min / suffix-min pair whose W-entry suffix
 //     array lives in registers (static indexing); the rightmost minimum uses max on the
 //     complemented key, exactly the reference's packing (src/sliding_min.rs:190-195,336-341);
-//   * the strand rule (src/canonical.rs) is evaluated only when leftmost != rightmost;
-//   * the low byte of the selected position and a flag bit per window are recorded in shared
-//     memory; mz_emit.cuh turns them into ordered, coalesced output.
+//   * leftmost != rightmost is only OR-accumulated per block; the strand rule
+//     (src/canonical.rs) runs in a cold fix-up for the few blocks that contain such a window;
+//   * the low byte of the selected position and a flag bit per window go to an L2-resident
+//     global scratch (coalesced rows); mz_emit.cuh turns them into ordered, coalesced output.
 #pragma once
 #include "../../include/mz_b200.h"
 #include <algorithm>
@@ -21,44 +25,78 @@
 namespace mz {
 
 constexpr uint32_t FAST_MAX_W = 32;
+constexpr uint32_t FAST_NT = 128;  // threads per block (compile-time: scratch strides are immediates)
 
-// Shared-memory layout (NT = blockDim.x, NB = van-Herk blocks per thread, WQ = ceil(W/4)):
-//   uint4 T[256]; uint32 misc[8]; emit staging; uint32 flagw[NB][NT]; uint32 recw[NB*WQ][NT]
+// Per-block scratch in GLOBAL memory (L2-resident: a few hundred KB per resident block, reused
+// for every tile the persistent block processes).  Row r, thread t -> word scratch[r*NT + t]:
+//   rows (b*(WQ+1) + 0)       flag word of van-Herk block b (bit t <-> window ending at element bW+t)
+//   rows (b*(WQ+1) + 1 + q)   low bytes of the selected positions of windows 4q..4q+3 of block b
 __host__ __device__ constexpr uint32_t fast_wq(uint32_t W) { return (W + 3) / 4; }
 __host__ __device__ inline uint32_t fast_nb(uint32_t S, uint32_t W) {
     return (S + 1 + (W - 1) + W - 1) / W;  // elements = S + has_prev + W - 1
 }
-inline size_t fast_smem(uint32_t NT, uint32_t S, uint32_t W) {
-    return 256 * 16 + 32 + EMIT_SMEM_BYTES + (size_t)fast_nb(S, W) * (1 + fast_wq(W)) * 4 * NT;
+// scratch words per WARP (a warp is an autonomous worker: tile = 32 threads x S windows)
+inline size_t fast_scratch_words(uint32_t S, uint32_t W) {
+    return (size_t)fast_nb(S, W) * (1 + fast_wq(W)) * 32;
+}
+constexpr uint32_t FAST_WARPS = FAST_NT / 32;
+constexpr uint32_t FAST_LIST = 32 * FAST_MAX_W;  // staging entries per warp (32 flag words x W bits)
+constexpr size_t FAST_SMEM = 256 * 16 + 32 + FAST_WARPS * FAST_LIST * 4;
+
+// Rare path (leftmost != rightmost minimum): strand rule 2*#TG > l on the window's l bases
+// (src/canonical.rs:19-29).  Kept out of line so the unrolled hot loop stays small.
+static __device__ __noinline__ bool window_prefers_left(const uint32_t* wbase, uint32_t sh0, uint32_t wlim,
+                                                 uint32_t lbit, uint32_t l) {
+    uint32_t p = sh0 + lbit, bits = 2u * l, cnt = 0;
+    while (bits) {
+        const uint32_t wl = p >> 5, sh = p & 31u;
+        const uint32_t w0 = __ldg(wbase + min(wl, wlim)), w1 = __ldg(wbase + min(wl + 1, wlim));
+        uint32_t v = __funnelshift_r(w0, w1, sh) & 0xAAAAAAAAu;
+        const uint32_t take = bits < 32u ? bits : 32u;
+        if (take < 32u) v &= (1u << take) - 1u;
+        cnt += __popc(v);
+        p += take;
+        bits -= take;
+    }
+    return 2u * cnt > l;
 }
 
-// 64 bits of the packed stream starting at bit position `bit`
-__device__ __forceinline__ void ld_bits64(const KArgs& a, uint64_t bit, uint32_t& lo, uint32_t& hi,
-                                          bool need_hi) {
-    uint64_t wi = bit >> 5;
-    uint32_t sh = (uint32_t)bit & 31u;
-    uint32_t w0 = ld_word(a, wi), w1 = ld_word(a, wi + 1);
-    lo = __funnelshift_r(w0, w1, sh);
-    hi = 0;
-    if (need_hi) {
-        uint32_t w2 = ld_word(a, wi + 2);
-        hi = __funnelshift_r(w1, w2, sh);
-    }
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+    uint4 v;
+    asm("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+    uint2 v;
+    asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+    return v;
+}
+// bf |= bit when a != b (forced to SETP + predicated OR: two issue slots)
+__device__ __forceinline__ void or_if_ne(uint32_t& bf, uint32_t a, uint32_t b, uint32_t bit) {
+    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bf) : "r"(a), "r"(b), "r"(bit));
+}
+// J is a compile-time constant after unrolling
+__device__ __forceinline__ uint32_t put_byte(uint32_t acc, uint32_t v, int J) {  // acc.byte[J] = v.byte[0]
+    return __byte_perm(acc, v, J == 0 ? 0x3214 : J == 1 ? 0x3240 : J == 2 ? 0x3410 : 0x4210);
+}
+__device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
+    return J == 0 ? (w & 0xffu) : J == 3 ? (w >> 24) : __byte_perm(w, 0, 0x4440 + J);
 }
 
 template <int W, bool HC, bool LR, bool SYNC>
-__global__ void __launch_bounds__(256) mz_fast_kernel(const KArgs a) {
+__global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
     constexpr int WQ = (W + 3) / 4;
+    constexpr uint32_t NT = FAST_NT;
+    constexpr uint32_t ROWS = WQ + 1;  // scratch rows per van-Herk block
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t NT = blockDim.x, tid = threadIdx.x;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint4* T = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* misc = reinterpret_cast<uint32_t*>(T + 256);
-    unsigned char* after = reinterpret_cast<unsigned char*>(misc + 8);
-    const EmitSmem es = EmitSmem::carve(after);
-    uint32_t* flagw = reinterpret_cast<uint32_t*>(after + EMIT_SMEM_BYTES);
-    const uint32_t NBmax = fast_nb(a.S, W);
-    uint32_t* recw = flagw + (size_t)NBmax * NT;
+    uint32_t* const list = misc + 8 + warp * FAST_LIST;  // this warp's staging list
+    // this warp's scratch rows: row r, lane t -> scr0[r*32 + t]
+    uint32_t* const scr0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * a.scratch_words_per_block;
+    uint32_t* const scr = scr0 + lane;
 
     const uint32_t k = a.k, R = a.rot & 31u, R2 = (2u * R) & 31u;
     // ---- table: index byte = in0 | in1<<2 | out0<<4 | out1<<6 (two consecutive bases) --------
@@ -71,7 +109,6 @@ __global__ void __launch_bounds__(256) mz_fast_kernel(const KArgs a) {
         T[idx] = make_uint4(f0, rotl32(f0, R) ^ f1, c0, rotr32(c0, R) ^ c1);
     }
     if (tid == 0) {
-        misc[0] = atomicAdd(a.ticket, 1u);
         uint32_t fa = 0, ca = 0;  // hash state of the virtual all-'A' k-mer before every segment
         for (uint32_t j = 0; j < k; j++) {
             fa ^= rotl32(a.f[0], (R * j) & 31u);
@@ -80,216 +117,353 @@ __global__ void __launch_bounds__(256) mz_fast_kernel(const KArgs a) {
         misc[1] = fa;
         misc[2] = ca;
     }
-    __syncthreads();
-    const uint32_t tile = misc[0];
-    const Segment sg = make_segment(a, tile, tid);
+    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T);
+    // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
+    const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (W - 1) / 2, so2 = a.mode == MODE_CLOSED ? W - 1 : (W - 1) / 2;
 
-    uint32_t cnt = 0, NB = 0;
-    if (sg.nvalid) {
-        uint32_t fw = misc[1], rc = misc[2];
-        // ---- prologue: k-1 bases, one at a time (leaving base = virtual 'A') -----------------
-        {
-            BaseReader in;
-            in.init(a, sg.bit0);
-            for (uint32_t u = 0; u + 1 < k; u++) {
-                const uint4 e = T[in.next(a)];
-                fw = rotl32(fw, R) ^ e.x;
-                if (HC) rc = rotr32(rc, R) ^ e.z;
-            }
-        }
-        const uint32_t nelem = sg.nvalid + sg.has_prev + (W - 1);
-        NB = (nelem + W - 1) / W;
-        uint32_t RL[W], RR[W];
-#pragma unroll
-        for (int t = 0; t < W; t++) RL[t] = 0xffffffffu, RR[t] = 0u;
-        uint32_t prev = 0xffffffffu;
-        // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
-        const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (W - 1) / 2, so2 = a.mode == MODE_CLOSED ? W - 1 : (W - 1) / 2;
-        // first/last valid window-end element: e = jl + W - 1, jl in [has_prev, has_prev + nvalid)
-        const uint32_t e_lo = sg.has_prev + (W - 1), e_hi = e_lo + sg.nvalid;
-        const uint64_t bit_in0 = sg.bit0 + 2ull * (k - 1);
+    __syncthreads();  // table + misc ready; from here on every warp works on its own
+    const bool minim = a.mode == MODE_MINIMIZER;
 
-        for (uint32_t b = 0; b < NB; b++) {
-            const uint32_t eb = b * W;
-            // entering bases: local bases k-1+eb .. ; leaving bases: local bases eb-1 ..
-            uint32_t x0, x1, y0, y1;
-            ld_bits64(a, bit_in0 + 2ull * eb, x0, x1, W > 16);
-            if (b == 0) {
-                ld_bits64(a, sg.bit0, y0, y1, W > 16);
-                y1 = __funnelshift_l(y0, y1, 2);  // shift the stream up by one base:
-                y0 <<= 2;                         // slot 0 leaves the virtual 'A'
-            } else {
-                ld_bits64(a, sg.bit0 + 2ull * (eb - 1), y0, y1, W > 16);
+    for (;;) {  // persistent: one tile (32 threads x S windows) per iteration, per warp
+        uint32_t tile = 0;
+        if (lane == 0) tile = atomicAdd(a.ticket, 1u);
+        tile = __shfl_sync(0xffffffffu, tile, 0);
+        if (tile >= a.num_tiles) break;
+        const Segment sg = make_segment_nt(a, tile, lane, 32u);
+
+        uint32_t cnt = 0, NB = 0;
+        if (sg.nvalid) {
+            uint32_t fw = misc[1], rc = misc[2];
+            // ---- prologue: k-1 bases, one at a time (leaving base = virtual 'A') -------------
+            {
+                BaseReader in;
+                in.init(a, sg.bit0);
+                for (uint32_t u = 0; u + 1 < k; u++) {
+                    const uint4 e = T[in.next(a)];
+                    fw = rotl32(fw, R) ^ e.x;
+                    if (HC) rc = rotr32(rc, R) ^ e.z;
+                }
             }
-            uint32_t N[4];
-            N[0] = (x0 & 0x0F0F0F0Fu) | ((y0 << 4) & 0xF0F0F0F0u);
-            N[1] = ((x0 >> 4) & 0x0F0F0F0Fu) | (y0 & 0xF0F0F0F0u);
-            if (W > 16) {
-                N[2] = (x1 & 0x0F0F0F0Fu) | ((y1 << 4) & 0xF0F0F0F0u);
-                N[3] = ((x1 >> 4) & 0x0F0F0F0Fu) | (y1 & 0xF0F0F0F0u);
-            }
-            uint32_t preL = 0, preR = 0, bf = 0, acc = 0;
-            uint32_t hpair = 0;
+            const uint32_t nelem = sg.nvalid + sg.has_prev + (W - 1);
+            NB = (nelem + W - 1) / W;
+            // first/last valid window-end element: e = jl + W - 1, jl in [has_prev, has_prev + nvalid)
+            const uint32_t e_lo = sg.has_prev + (W - 1), e_hi = e_lo + sg.nvalid;
+
+            // ---- thread-local view of the packed stream (32-bit word offsets) ----------------
+            // Entering bases of block b start at local base k-1+bW; leaving bases at local base
+            // bW-1 (base -1 = virtual 'A').  Both are addressed with one extra virtual word in
+            // front (+32 bits) so that the bit position never goes negative.
+            const uint64_t w0abs = sg.bit0 >> 5;
+            const uint32_t* const wbase = a.seq + w0abs;
+            const uint32_t sh0 = (uint32_t)sg.bit0 & 31u;
+            const uint64_t remw = a.seq_nwords - 1 - w0abs;
+            const uint32_t wlim = remw > 0x7ffffff0ull ? 0x7ffffff0u : (uint32_t)remw;
+            uint32_t pin = sh0 + 32u + 2u * (k - 1);  // bit position (+32) of the entering stream
+            uint32_t pout = sh0 + 30u;                // bit position (+32) of the leaving stream
+            // may any (pre)fetch of this thread touch a word past the end of the buffer?
+            const bool clampd = ((pin + 2u * (NB + 1) * W) >> 5) + 2u > wlim;
+            auto ldw = [&](uint32_t wl1) -> uint32_t {  // wl1 = word offset + 1 (virtual word 0)
+                if (wl1 == 0) return 0u;
+                uint32_t wl = wl1 - 1;
+                if (clampd) wl = min(wl, wlim);
+                return __ldg(wbase + wl);
+            };
+            uint32_t iw0 = ldw(pin >> 5), iw1 = ldw((pin >> 5) + 1), iw2 = W > 16 ? ldw((pin >> 5) + 2) : 0u;
+            uint32_t ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1), ow2 = W > 16 ? ldw((pout >> 5) + 2) : 0u;
+            ow0 &= ~(3u << (pout & 31u));  // element 0 leaves the virtual 'A'
+
+            uint32_t RL[W], RR[W];
 #pragma unroll
-            for (int t = 0; t < W; t++) {
-                uint32_t h;
-                if ((t & 1) == 0) {
-                    const uint32_t word = N[(t >> 4) * 2 + ((t >> 1) & 1)];
-                    const int byte = (t & 15) >> 2;
-                    const uint32_t idx = byte == 0 ? (word & 0xffu)
-                                       : byte == 3 ? (word >> 24)
-                                                   : __byte_perm(word, 0, 0x4440 + byte);
-                    if (HC) {
-                        const uint4 e = T[idx];
-                        const uint32_t fA = rotl32(fw, R) ^ e.x, rA = rotr32(rc, R) ^ e.z;
-                        h = fA + rA;
-                        if (t + 1 < W) {
-                            fw = rotl32(fw, R2) ^ e.y;
-                            rc = rotr32(rc, R2) ^ e.w;
-                            hpair = fw + rc;
+            for (int t = 0; t < W; t++) RL[t] = 0xffffffffu, RR[t] = 0u;
+            uint32_t prev = 0xffffffffu, prevlow = 0x100u;
+            uint32_t* sp = scr;
+
+            for (uint32_t b = 0; b < NB; b++) {
+                const uint32_t eb = b * W;
+                const uint32_t shi = pin & 31u, sho = pout & 31u;
+                const uint32_t x0 = __funnelshift_r(iw0, iw1, shi), x1 = W > 16 ? __funnelshift_r(iw1, iw2, shi) : 0u;
+                const uint32_t y0 = __funnelshift_r(ow0, ow1, sho), y1 = W > 16 ? __funnelshift_r(ow1, ow2, sho) : 0u;
+                // prefetch the next block's words (consumed ~W*30 instructions later)
+                pin += 2u * W;
+                pout += 2u * W;
+                if (!clampd) {
+                    const uint32_t* pi = wbase + (pin >> 5) - 1;
+                    const uint32_t* po = wbase + (pout >> 5) - 1;
+                    iw0 = __ldg(pi), iw1 = __ldg(pi + 1);
+                    ow0 = __ldg(po), ow1 = __ldg(po + 1);
+                    if (W > 16) iw2 = __ldg(pi + 2), ow2 = __ldg(po + 2);
+                } else {
+                    iw0 = ldw(pin >> 5), iw1 = ldw((pin >> 5) + 1);
+                    ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1);
+                    if (W > 16) iw2 = ldw((pin >> 5) + 2), ow2 = ldw((pout >> 5) + 2);
+                }
+                uint32_t N[4];
+                N[0] = (x0 & 0x0F0F0F0Fu) | ((y0 << 4) & 0xF0F0F0F0u);
+                N[1] = ((x0 >> 4) & 0x0F0F0F0Fu) | (y0 & 0xF0F0F0F0u);
+                if (W > 16) {
+                    N[2] = (x1 & 0x0F0F0F0Fu) | ((y1 << 4) & 0xF0F0F0F0u);
+                    N[3] = ((x1 >> 4) & 0x0F0F0F0Fu) | (y1 & 0xF0F0F0F0u);
+                }
+                uint32_t preL = 0, preR = 0, bf = 0, tacc = 0, lastR = 0;
+                uint32_t accL[WQ], accR[WQ];
+#pragma unroll
+                for (int q = 0; q < WQ; q++) accL[q] = 0, accR[q] = 0;
+                uint32_t hpair = 0;
+#pragma unroll
+                for (int t = 0; t < W; t++) {
+                    uint32_t h;
+                    if ((t & 1) == 0) {
+                        const uint32_t word = N[(t >> 4) * 2 + ((t >> 1) & 1)];
+                        const uint32_t idx = get_byte(word, (t & 15) >> 2);
+                        const uint32_t addr = idx * 16u + tb;
+                        if (HC) {
+                            const uint4 e = lds128(addr);
+                            const uint32_t fA = rotl32(fw, R) ^ e.x, rA = rotr32(rc, R) ^ e.z;
+                            h = fA + rA;
+                            if (t + 1 < W) {
+                                fw = rotl32(fw, R2) ^ e.y;
+                                rc = rotr32(rc, R2) ^ e.w;
+                                hpair = fw + rc;
+                            } else {
+                                fw = fA;
+                                rc = rA;
+                            }
                         } else {
-                            fw = fA;
-                            rc = rA;
+                            const uint2 e = lds64(addr);
+                            const uint32_t fA = rotl32(fw, R) ^ e.x;
+                            h = fA;
+                            if (t + 1 < W) {
+                                fw = rotl32(fw, R2) ^ e.y;
+                                hpair = fw;
+                            } else {
+                                fw = fA;
+                            }
                         }
                     } else {
-                        const uint2 e = *reinterpret_cast<const uint2*>(&T[idx]);
-                        const uint32_t fA = rotl32(fw, R) ^ e.x;
-                        h = fA;
-                        if (t + 1 < W) {
-                            fw = rotl32(fw, R2) ^ e.y;
-                            hpair = fw;
+                        h = hpair;
+                    }
+                    const uint32_t pos = eb + t;
+                    const uint32_t le = (h & 0xffff0000u) | pos;
+                    preL = t == 0 ? le : min(preL, le);
+                    const uint32_t res = t < W - 1 ? min(preL, RL[t < W - 1 ? t + 1 : 0]) : preL;
+                    RL[t] = le;
+                    if (LR) {
+                        const uint32_t re = le ^ 0xffff0000u;
+                        preR = t == 0 ? re : max(preR, re);
+                        const uint32_t mR = t < W - 1 ? max(preR, RR[t < W - 1 ? t + 1 : 0]) : preR;
+                        RR[t] = re;
+                        tacc |= res ^ mR;  // low half != 0  <=>  leftmost != rightmost
+                        accR[t >> 2] = put_byte(accR[t >> 2], mR, t & 3);
+                        if (t == W - 1) lastR = mR;
+                    }
+                    if (SYNC) {
+                        const uint32_t d = pos - (res & 0xffffu);
+                        if (d == so1 || d == so2) bf |= 1u << t;
+                    } else {
+                        or_if_ne(bf, res, prev, 1u << t);
+                        prev = res;
+                    }
+                    accL[t >> 2] = put_byte(accL[t >> 2], res, t & 3);
+                }
+                // suffix minima of this block (slot 0 is never needed)
+#pragma unroll
+                for (int q = W - 2; q >= 1; q--) {
+                    RL[q] = min(RL[q], RL[q + 1]);
+                    if (LR) RR[q] = max(RR[q], RR[q + 1]);
+                }
+                if (LR && (tacc & 0xffffu) != 0u) {
+                    // cold: some window of this block has leftmost != rightmost.  Apply the strand
+                    // rule to those windows and rebuild the block's flags from the position bytes.
+                    bf = 0;
+                    uint32_t pl = prevlow;
+#pragma unroll
+                    for (int t = 0; t < W; t++) {
+                        uint32_t cur = get_byte(accL[t >> 2], t & 3);
+                        const uint32_t rgt = get_byte(accR[t >> 2], t & 3);
+                        if (cur != rgt && eb + t >= (uint32_t)(W - 1)) {
+                            if (!window_prefers_left(wbase, sh0, wlim, 2u * (eb + t - (W - 1)), a.l)) {
+                                cur = rgt;
+                                accL[t >> 2] = put_byte(accL[t >> 2], rgt, t & 3);
+                                if (t == W - 1) prev = lastR ^ 0xffff0000u;
+                            }
+                        }
+                        if (SYNC) {
+                            const uint32_t d = (eb + t - cur) & 0xffu;
+                            if (d == so1 || d == so2) bf |= 1u << t;
                         } else {
-                            fw = fA;
+                            if (cur != pl) bf |= 1u << t;
+                            pl = cur;
                         }
                     }
-                } else {
-                    h = hpair;
                 }
-                const uint32_t pos = eb + t;
-                const uint32_t le = (h & 0xffff0000u) | pos;
-                preL = t == 0 ? le : min(preL, le);
-                uint32_t res = t < W - 1 ? min(preL, RL[t < W - 1 ? t + 1 : 0]) : preL;
-                RL[t] = le;
-                if (LR) {
-                    const uint32_t re = le ^ 0xffff0000u;
-                    preR = t == 0 ? re : max(preR, re);
-                    const uint32_t mR = t < W - 1 ? max(preR, RR[t < W - 1 ? t + 1 : 0]) : preR;
-                    RR[t] = re;
-                    if (((res ^ mR) & 0xffffu) != 0u && pos >= (uint32_t)(W - 1)) {
-                        // leftmost != rightmost: strand rule on the window's l bases
-                        const uint32_t tg = tg_count(a, sg.bit0 + 2ull * (pos - (W - 1)), a.l);
-                        if (!(2u * tg > a.l)) res = mR ^ 0xffff0000u;
-                    }
+                prevlow = get_byte(accL[(W - 1) >> 2], (W - 1) & 3);
+                // keep flags of valid windows only: bit t <-> window-end element eb + t
+                {
+                    const uint32_t lo = e_lo > eb ? min(e_lo - eb, (uint32_t)W) : 0u;
+                    const uint32_t hi = e_hi > eb ? min(e_hi - eb, (uint32_t)W) : 0u;
+                    const uint32_t mhi = hi >= 32u ? 0xffffffffu : ((1u << hi) - 1u);
+                    const uint32_t mlo = lo >= 32u ? 0xffffffffu : ((1u << lo) - 1u);
+                    if (!SYNC && sg.first_always && e_lo >= eb && e_lo < eb + W) bf |= 1u << (e_lo - eb);
+                    bf &= mhi & ~mlo;
                 }
-                bool flag;
-                if (SYNC) {
-                    const uint32_t d = pos - (res & 0xffffu);
-                    flag = d == so1 || d == so2;
-                } else {
-                    flag = res != prev;
-                    prev = res;
-                }
-                if (flag) bf |= 1u << t;
-                acc = __byte_perm(acc, res, (t & 3) == 0 ? 0x3214 : (t & 3) == 1 ? 0x3240 : (t & 3) == 2 ? 0x3410 : 0x4210);
-                if ((t & 3) == 3 || t == W - 1) recw[((size_t)b * WQ + (t >> 2)) * NT + tid] = acc;
-            }
-            // suffix minima of this block (slot 0 is never needed)
+                sp[0] = bf;
 #pragma unroll
-            for (int q = W - 2; q >= 1; q--) {
-                RL[q] = min(RL[q], RL[q + 1]);
-                if (LR) RR[q] = max(RR[q], RR[q + 1]);
+                for (int q = 0; q < WQ; q++) sp[(1 + q) * 32] = accL[q];
+                sp += ROWS * 32;
+                cnt += __popc(bf);
             }
-            // keep flags of valid windows only: bit t <-> window-end element eb + t
-            {
-                const uint32_t lo = e_lo > eb ? min(e_lo - eb, (uint32_t)W) : 0u;
-                const uint32_t hi = e_hi > eb ? min(e_hi - eb, (uint32_t)W) : 0u;
-                const uint32_t mhi = hi >= 32u ? 0xffffffffu : ((1u << hi) - 1u);
-                const uint32_t mlo = lo >= 32u ? 0xffffffffu : ((1u << lo) - 1u);
-                if (!SYNC && sg.first_always && e_lo >= eb && e_lo < eb + W) bf |= 1u << (e_lo - eb);
-                bf &= mhi & ~mlo;
+        }
+        // ---- ordered emission, warp-autonomous (no block barriers) ---------------------------
+        __syncwarp();
+        uint32_t inc = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= (uint32_t)o) inc += v;
+        }
+        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+        const unsigned long long gbase = lookback_warp0(a.tile_state, tile, total);
+        if (lane == 0 && tile == a.num_tiles - 1) *a.count_out = gbase + total;
+        const bool ovf = gbase + total > a.cap;
+        if (ovf && lane == 0) *a.overflow = 1u;
+        if (a.n_reads != 0) {
+            const uint64_t r = (uint64_t)tile * 32u + lane;
+            if (r < a.n_reads) {
+                a.out_offsets[r + 1] = gbase + inc;
+                if (r == 0) a.out_offsets[0] = 0;
             }
-            flagw[(size_t)b * NT + tid] = bf;
-            cnt += __popc(bf);
+        }
+        if (ovf || total == 0) continue;
+
+        uint32_t NBw = NB;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) NBw = max(NBw, __shfl_xor_sync(0xffffffffu, NBw, o));
+        const bool canon_val = a.val_canonical != 0;
+        const uint64_t j00 = a.wbeg + (uint64_t)tile * 32u * a.S;  // first window of the tile
+        unsigned long long cursor = gbase;
+        const uint32_t nitems = 32u * NBw;
+        // items = (owner lane t, van-Herk block b) in output order; 32 flag words per round
+        for (uint32_t i0 = 0; i0 < nitems; i0 += 32) {
+            const uint32_t i = i0 + lane, t = i / NBw, b = i - t * NBw;
+            const uint32_t nb_t = __shfl_sync(0xffffffffu, NB, t);
+            uint32_t f = b < nb_t ? __ldcg(scr0 + (size_t)(b * ROWS) * 32 + t) : 0u;
+            const uint32_t pc = __popc(f);
+            uint32_t pin = pc;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, pin, o);
+                if (lane >= (uint32_t)o) pin += v;
+            }
+            const uint32_t tot = __shfl_sync(0xffffffffu, pin, 31);
+            if (tot == 0) continue;
+            uint32_t o = pin - pc;
+            while (f) {
+                const uint32_t bit = (uint32_t)__ffs(f) - 1u;
+                f &= f - 1u;
+                list[o++] = (t << 16) | (b * W + bit);
+            }
+            __syncwarp();
+            for (uint32_t x = lane; x < tot; x += 32) {
+                const uint32_t dsc = list[x];
+                const uint32_t t2 = dsc >> 16, e = dsc & 0xffffu, b2 = e / W, bit2 = e - b2 * W;
+                const uint32_t wv = __ldcg(scr0 + (size_t)(b2 * ROWS + 1 + (bit2 >> 2)) * 32 + t2);
+                const uint32_t lowb = (wv >> (8u * (bit2 & 3u))) & 0xffu;
+                const uint32_t jl = e - (W - 1);  // local window index of the owner
+                uint64_t pos_base, win_base, bit0;
+                uint32_t hp;
+                if (a.n_reads == 0) {
+                    const uint64_t j0 = j00 + (uint64_t)t2 * a.S;
+                    hp = (j0 > 0 && minim) ? 1u : 0u;
+                    pos_base = j0 - hp;
+                    win_base = j0;
+                    bit0 = (uint64_t)((int64_t)(2 * pos_base) + a.bitbias);
+                } else {
+                    const Segment og = make_segment_nt(a, tile, t2, 32u);
+                    hp = 0, pos_base = 0, win_base = 0, bit0 = og.bit0;
+                }
+                const uint32_t jv = jl - hp;
+                const uint32_t local = minim ? jl + ((lowb - jl) & 0xffu) : jl;
+                const unsigned long long oi = cursor + x;
+                a.pos[oi] = (uint32_t)(pos_base + local);
+                if (a.want_sk) a.sk[oi] = (uint32_t)(win_base + jv);
+                if (a.value_bits == 64) {
+                    a.val[oi] = kmer_value_u64(a, bit0 + 2ull * local, a.val_len, canon_val);
+                } else if (a.value_bits == 128) {
+                    uint64_t lo, hi;
+                    kmer_value_u128(a, bit0 + 2ull * local, a.val_len, canon_val, lo, hi);
+                    reinterpret_cast<ulonglong2*>(a.val)[oi] = make_ulonglong2(lo, hi);
+                }
+            }
+            cursor += tot;
+            __syncwarp();
         }
     }
-    emit_phase(a, sg, tile, cnt, flagw, NB, es,
-               [&](uint32_t q, uint32_t bit, uint32_t& jv, uint32_t& d) {
-                   const uint32_t e = q * W + bit;  // window-end element
-                   const uint32_t jl = e - (W - 1);
-                   jv = jl - sg.has_prev;
-                   const uint32_t wv = recw[((size_t)q * WQ + (bit >> 2)) * NT + tid];
-                   const uint32_t lowb = (wv >> (8u * (bit & 3u))) & 0xffu;
-                   d = (lowb - jl) & 0xffu;  // selected k-mer index is in [jl, jl + W)
-               });
 }
 
 // ---- host side ---------------------------------------------------------------------------
+struct FastPlan {
+    uint32_t S = 0, num_tiles = 0, grid = 0;
+    size_t scratch_words_per_block = 0;
+};
+
 // Geometry for the fast kernel; returns false when (k, w, ...) is outside its domain.
-inline bool plan_fast(int sm_count, size_t smem_optin, const mz_params& p, uint64_t nwin,
-                      uint32_t* NT, uint32_t* S, size_t* smem, uint32_t* num_tiles) {
+inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan* pl) {
     if (p.w > FAST_MAX_W) return false;
     if (p.hash_canonical && !p.strand_tiebreak) return false;  // rare combo -> generic kernel
-    const char* env_nt = getenv("MZ_FAST_NT");
     const char* env_s = getenv("MZ_FAST_S");
-    uint32_t nt = env_nt ? (uint32_t)atoi(env_nt) : 128u;
-    if (nt != 64 && nt != 128 && nt != 256) nt = 128;
-    const size_t budget = std::min<size_t>(smem_optin, 220 * 1024);
+    const char* env_bps = getenv("MZ_FAST_BPS");
+    const uint32_t bps = env_bps ? (uint32_t)atoi(env_bps) : 4u;  // resident blocks per SM (target)
+    const uint64_t slots = (uint64_t)sm_count * bps * FAST_WARPS;  // resident warps
     uint32_t s;
     if (env_s) {
         s = (uint32_t)atoi(env_s);
     } else {
-        // enough tiles to fill the machine a few times over, S in [64, 416]
-        uint64_t target_tiles = (uint64_t)sm_count * 8;
-        uint64_t want = (nwin + target_tiles * nt - 1) / (target_tiles * nt);
-        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 416);
+        // long segments amortise the (k+w-2)-base warm-up; keep >= ~3 tiles per resident block
+        uint64_t want = nwin / (slots * 3 * 32);
+        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 1024);
     }
     s = std::max<uint32_t>(16, (s + 15) / 16 * 16);
-    while (s > 16 && fast_smem(nt, s, p.w) > budget / 3) s -= 16;
-    if (fast_smem(nt, s, p.w) > budget) return false;
     if ((uint64_t)s + p.w + 2 >= 65535) return false;
-    const uint64_t Tt = (uint64_t)nt * s;
+    const uint64_t Tt = (uint64_t)32 * s;
     const uint64_t tiles = (nwin + Tt - 1) / Tt;
     if (tiles == 0 || tiles > 0x7fffffffull) return false;
-    *NT = nt, *S = s, *smem = fast_smem(nt, s, p.w), *num_tiles = (uint32_t)tiles;
+    pl->S = s;
+    pl->num_tiles = (uint32_t)tiles;
+    pl->grid = (uint32_t)std::min<uint64_t>((tiles + FAST_WARPS - 1) / FAST_WARPS, (uint64_t)sm_count * bps);
+    pl->scratch_words_per_block = fast_scratch_words(s, p.w);
     return true;
 }
 
 template <int W, bool HC, bool LR, bool SYNC>
-inline int launch_fast_inst(uint32_t NT, size_t smem, uint32_t tiles, const KArgs& a, cudaStream_t st) {
+inline int launch_fast_inst(uint32_t grid, const KArgs& a, cudaStream_t st) {
     auto kern = mz_fast_kernel<W, HC, LR, SYNC>;
-    if (smem > 48 * 1024) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return MZ_ERR_CUDA;
-    }
-    kern<<<tiles, NT, smem, st>>>(a);
+    kern<<<grid, FAST_NT, FAST_SMEM, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? MZ_OK : MZ_ERR_CUDA;
 }
 
 template <int W>
-inline int launch_fast_w(const mz_params& p, uint32_t NT, size_t smem, uint32_t tiles, const KArgs& a,
-                         cudaStream_t st) {
+inline int launch_fast_w(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
     const bool sync = p.mode != MZ_MODE_MINIMIZER;
     if (p.strand_tiebreak) {
-        return sync ? launch_fast_inst<W, true, true, true>(NT, smem, tiles, a, st)
-                    : launch_fast_inst<W, true, true, false>(NT, smem, tiles, a, st);
+        return sync ? launch_fast_inst<W, true, true, true>(grid, a, st)
+                    : launch_fast_inst<W, true, true, false>(grid, a, st);
     }
-    return sync ? launch_fast_inst<W, false, false, true>(NT, smem, tiles, a, st)
-                : launch_fast_inst<W, false, false, false>(NT, smem, tiles, a, st);
+    return sync ? launch_fast_inst<W, false, false, true>(grid, a, st)
+                : launch_fast_inst<W, false, false, false>(grid, a, st);
 }
 
 // defined in mz_fast_g{0..3}.cu (W = 1..8, 9..16, 17..24, 25..32)
-int launch_fast_g0(const mz_params&, uint32_t, size_t, uint32_t, const KArgs&, cudaStream_t);
-int launch_fast_g1(const mz_params&, uint32_t, size_t, uint32_t, const KArgs&, cudaStream_t);
-int launch_fast_g2(const mz_params&, uint32_t, size_t, uint32_t, const KArgs&, cudaStream_t);
-int launch_fast_g3(const mz_params&, uint32_t, size_t, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_g0(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_g1(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_g2(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_g3(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 
-inline int launch_fast(const mz_params& p, uint32_t NT, size_t smem, uint32_t tiles, const KArgs& a,
-                       cudaStream_t st) {
+inline int launch_fast(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
     switch ((p.w - 1) / 8) {
-        case 0: return launch_fast_g0(p, NT, smem, tiles, a, st);
-        case 1: return launch_fast_g1(p, NT, smem, tiles, a, st);
-        case 2: return launch_fast_g2(p, NT, smem, tiles, a, st);
-        case 3: return launch_fast_g3(p, NT, smem, tiles, a, st);
+        case 0: return launch_fast_g0(p, grid, a, st);
+        case 1: return launch_fast_g1(p, grid, a, st);
+        case 2: return launch_fast_g2(p, grid, a, st);
+        case 3: return launch_fast_g3(p, grid, a, st);
         default: return MZ_ERR_UNSUPPORTED;
     }
 }

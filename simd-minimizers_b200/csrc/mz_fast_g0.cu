@@ -2,17 +2,16 @@
 // units so the build parallelises).
 #include "mz_fast.cuh"
 namespace mz {
-int launch_fast_g0(const mz_params& p, uint32_t NT, size_t smem, uint32_t tiles, const KArgs& a,
-                    cudaStream_t st) {
+int launch_fast_g0(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
     switch (p.w) {
-        case 1: return launch_fast_w<1>(p, NT, smem, tiles, a, st);
-        case 2: return launch_fast_w<2>(p, NT, smem, tiles, a, st);
-        case 3: return launch_fast_w<3>(p, NT, smem, tiles, a, st);
-        case 4: return launch_fast_w<4>(p, NT, smem, tiles, a, st);
-        case 5: return launch_fast_w<5>(p, NT, smem, tiles, a, st);
-        case 6: return launch_fast_w<6>(p, NT, smem, tiles, a, st);
-        case 7: return launch_fast_w<7>(p, NT, smem, tiles, a, st);
-        case 8: return launch_fast_w<8>(p, NT, smem, tiles, a, st);
+        case 1: return launch_fast_w<1>(p, grid, a, st);
+        case 2: return launch_fast_w<2>(p, grid, a, st);
+        case 3: return launch_fast_w<3>(p, grid, a, st);
+        case 4: return launch_fast_w<4>(p, grid, a, st);
+        case 5: return launch_fast_w<5>(p, grid, a, st);
+        case 6: return launch_fast_w<6>(p, grid, a, st);
+        case 7: return launch_fast_w<7>(p, grid, a, st);
+        case 8: return launch_fast_w<8>(p, grid, a, st);
         default: return MZ_ERR_UNSUPPORTED;
     }
 }

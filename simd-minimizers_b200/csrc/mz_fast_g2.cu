@@ -2,17 +2,16 @@
 // units so the build parallelises).
 #include "mz_fast.cuh"
 namespace mz {
-int launch_fast_g2(const mz_params& p, uint32_t NT, size_t smem, uint32_t tiles, const KArgs& a,
-                    cudaStream_t st) {
+int launch_fast_g2(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
     switch (p.w) {
-        case 17: return launch_fast_w<17>(p, NT, smem, tiles, a, st);
-        case 18: return launch_fast_w<18>(p, NT, smem, tiles, a, st);
-        case 19: return launch_fast_w<19>(p, NT, smem, tiles, a, st);
-        case 20: return launch_fast_w<20>(p, NT, smem, tiles, a, st);
-        case 21: return launch_fast_w<21>(p, NT, smem, tiles, a, st);
-        case 22: return launch_fast_w<22>(p, NT, smem, tiles, a, st);
-        case 23: return launch_fast_w<23>(p, NT, smem, tiles, a, st);
-        case 24: return launch_fast_w<24>(p, NT, smem, tiles, a, st);
+        case 17: return launch_fast_w<17>(p, grid, a, st);
+        case 18: return launch_fast_w<18>(p, grid, a, st);
+        case 19: return launch_fast_w<19>(p, grid, a, st);
+        case 20: return launch_fast_w<20>(p, grid, a, st);
+        case 21: return launch_fast_w<21>(p, grid, a, st);
+        case 22: return launch_fast_w<22>(p, grid, a, st);
+        case 23: return launch_fast_w<23>(p, grid, a, st);
+        case 24: return launch_fast_w<24>(p, grid, a, st);
         default: return MZ_ERR_UNSUPPORTED;
     }
 }

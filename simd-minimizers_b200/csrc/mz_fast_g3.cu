@@ -2,17 +2,16 @@
 // units so the build parallelises).
 #include "mz_fast.cuh"
 namespace mz {
-int launch_fast_g3(const mz_params& p, uint32_t NT, size_t smem, uint32_t tiles, const KArgs& a,
-                    cudaStream_t st) {
+int launch_fast_g3(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
     switch (p.w) {
-        case 25: return launch_fast_w<25>(p, NT, smem, tiles, a, st);
-        case 26: return launch_fast_w<26>(p, NT, smem, tiles, a, st);
-        case 27: return launch_fast_w<27>(p, NT, smem, tiles, a, st);
-        case 28: return launch_fast_w<28>(p, NT, smem, tiles, a, st);
-        case 29: return launch_fast_w<29>(p, NT, smem, tiles, a, st);
-        case 30: return launch_fast_w<30>(p, NT, smem, tiles, a, st);
-        case 31: return launch_fast_w<31>(p, NT, smem, tiles, a, st);
-        case 32: return launch_fast_w<32>(p, NT, smem, tiles, a, st);
+        case 25: return launch_fast_w<25>(p, grid, a, st);
+        case 26: return launch_fast_w<26>(p, grid, a, st);
+        case 27: return launch_fast_w<27>(p, grid, a, st);
+        case 28: return launch_fast_w<28>(p, grid, a, st);
+        case 29: return launch_fast_w<29>(p, grid, a, st);
+        case 30: return launch_fast_w<30>(p, grid, a, st);
+        case 31: return launch_fast_w<31>(p, grid, a, st);
+        case 32: return launch_fast_w<32>(p, grid, a, st);
         default: return MZ_ERR_UNSUPPORTED;
     }
 }

@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
             cnt += __popc(flags);
         }
     }
-    emit_phase(a, sg, tile, cnt, flagw, (sg.nvalid + 31u) / 32u, es,
+    emit_phase(a, sg, tile, cnt, flagw, 1u, (sg.nvalid + 31u) / 32u, es,
                [&](uint32_t q, uint32_t bit, uint32_t& jv, uint32_t& d) {
                    jv = q * 32u + bit;
                    d = (uint32_t)rec[jv * NT + tid] - (jv + sg.has_prev);
