@@ -177,7 +177,7 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
         pl.fast = true;
         pl.S = fp.S;
         pl.num_tiles = fp.num_tiles;
-        if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS))) return rc;
+        if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS * 2))) return rc;
         a.scratch = d.rows.p;
         a.scratch_words_per_block = fp.scratch_words_per_block;
     } else {

@@ -188,9 +188,11 @@ __device__ __forceinline__ unsigned long long lookback_warp0(unsigned long long*
         int64_t idx = base - (int64_t)lane;
         unsigned long long v = 2ull;  // virtual tile before 0: inclusive prefix 0
         if (idx >= 0) {
-            do {
+            v = ld_state(state + idx);
+            while ((v & 3ull) == 0ull) {
+                __nanosleep(64);
                 v = ld_state(state + idx);
-            } while ((v & 3ull) == 0ull);
+            }
         }
         uint32_t is_prefix = __ballot_sync(0xffffffffu, (v & 3ull) == 2ull);
         uint32_t first = is_prefix ? (uint32_t)__ffs(is_prefix) - 1u : 32u;
@@ -200,6 +202,38 @@ __device__ __forceinline__ unsigned long long lookback_warp0(unsigned long long*
         excl += contrib;
         if (is_prefix) break;
         base -= 32;
+    }
+    if (lane == 0) st_state(state + tile, ((excl + total) << 2) | 2ull);
+    return excl;
+}
+
+// Variant for pipelined tiles: the tile's aggregate (status 1) has ALREADY been published; walk
+// back to find the exclusive prefix, then publish the inclusive prefix.  Called by a whole warp.
+__device__ __forceinline__ unsigned long long lookback_excl(unsigned long long* state, uint32_t tile,
+                                                            unsigned long long total) {
+    const uint32_t lane = threadIdx.x & 31u;
+    unsigned long long excl = 0;
+    if (tile != 0) {
+        int64_t base = (int64_t)tile - 1;
+        while (true) {
+            int64_t idx = base - (int64_t)lane;
+            unsigned long long v = 2ull;  // virtual tile before 0: inclusive prefix 0
+            if (idx >= 0) {
+                v = ld_state(state + idx);
+                while ((v & 3ull) == 0ull) {
+                    __nanosleep(64);
+                    v = ld_state(state + idx);
+                }
+            }
+            uint32_t is_prefix = __ballot_sync(0xffffffffu, (v & 3ull) == 2ull);
+            uint32_t first = is_prefix ? (uint32_t)__ffs(is_prefix) - 1u : 32u;
+            unsigned long long contrib = (lane <= first) ? (v >> 2) : 0ull;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+            excl += contrib;
+            if (is_prefix) break;
+            base -= 32;
+        }
     }
     if (lane == 0) st_state(state + tile, ((excl + total) << 2) | 2ull);
     return excl;

@@ -29,19 +29,22 @@ constexpr uint32_t FAST_NT = 128;  // threads per block (compile-time: scratch s
 
 // Per-block scratch in GLOBAL memory (L2-resident: a few hundred KB per resident block, reused
 // for every tile the persistent block processes).  Row r, thread t -> word scratch[r*NT + t]:
-//   rows (b*(WQ+1) + 0)       flag word of van-Herk block b (bit t <-> window ending at element bW+t)
-//   rows (b*(WQ+1) + 1 + q)   low bytes of the selected positions of windows 4q..4q+3 of block b
+//   rows (b*WQ + q)   low bytes of the selected positions of windows 4q..4q+3 of van-Herk block b
+// The flag word of block b (bit t <-> window ending at element bW+t) stays in shared memory.
 __host__ __device__ constexpr uint32_t fast_wq(uint32_t W) { return (W + 3) / 4; }
 __host__ __device__ inline uint32_t fast_nb(uint32_t S, uint32_t W) {
     return (S + 1 + (W - 1) + W - 1) / W;  // elements = S + has_prev + W - 1
 }
 // scratch words per WARP (a warp is an autonomous worker: tile = 32 threads x S windows)
 inline size_t fast_scratch_words(uint32_t S, uint32_t W) {
-    return (size_t)fast_nb(S, W) * (1 + fast_wq(W)) * 32;
+    return (size_t)fast_nb(S, W) * fast_wq(W) * 32;
 }
 constexpr uint32_t FAST_WARPS = FAST_NT / 32;
-constexpr uint32_t FAST_LIST = 32 * FAST_MAX_W;  // staging entries per warp (32 flag words x W bits)
-constexpr size_t FAST_SMEM = 256 * 16 + 32 + FAST_WARPS * FAST_LIST * 4;
+constexpr uint32_t FAST_LIST = 1024;  // staging entries per warp and pass
+// shared memory: table | misc | per-warp staging list | per-warp flag words (2 tiles in flight)
+inline size_t fast_smem(uint32_t S, uint32_t W) {
+    return 256 * 16 + 32 + FAST_WARPS * FAST_LIST * 4 + (size_t)FAST_WARPS * 2 * fast_nb(S, W) * 32 * 4;
+}
 
 // Rare path (leftmost != rightmost minimum): strand rule 2*#TG > l on the window's l bases
 // (src/canonical.rs:19-29).  Kept out of line so the unrolled hot loop stays small.
@@ -88,15 +91,16 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
     constexpr int WQ = (W + 3) / 4;
     constexpr uint32_t NT = FAST_NT;
-    constexpr uint32_t ROWS = WQ + 1;  // scratch rows per van-Herk block
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint4* T = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* misc = reinterpret_cast<uint32_t*>(T + 256);
     uint32_t* const list = misc + 8 + warp * FAST_LIST;  // this warp's staging list
-    // this warp's scratch rows: row r, lane t -> scr0[r*32 + t]
-    uint32_t* const scr0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * a.scratch_words_per_block;
-    uint32_t* const scr = scr0 + lane;
+    const uint32_t NBmax = fast_nb(a.S, W);
+    // flag words of this warp, two tiles in flight: fl0[buf][b*32 + lane]
+    uint32_t* const fl0 = misc + 8 + FAST_WARPS * FAST_LIST + (size_t)warp * 2 * NBmax * 32;
+    // this warp's record rows in global scratch (two buffers): row r, lane t -> sc0[buf][r*32 + t]
+    uint32_t* const sc0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * 2 * a.scratch_words_per_block;
 
     const uint32_t k = a.k, R = a.rot & 31u, R2 = (2u * R) & 31u;
     // ---- table: index byte = in0 | in1<<2 | out0<<4 | out1<<6 (two consecutive bases) --------
@@ -124,14 +128,20 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
     __syncthreads();  // table + misc ready; from here on every warp works on its own
     const bool minim = a.mode == MODE_MINIMIZER;
 
+    // Software pipeline over tiles: the look-back + emission of tile A runs after the main loop
+    // of the next tile B, so A's predecessors have published their counts by then.
+    uint32_t p_valid = 0, p_tile = 0, p_cnt = 0, p_NB = 0, p_inc = 0, cur = 0;
     for (;;) {  // persistent: one tile (32 threads x S windows) per iteration, per warp
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(a.ticket, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
-        if (tile >= a.num_tiles) break;
+        const bool have = tile < a.num_tiles;
+        uint32_t cnt = 0, NB = 0, inc = 0;
+        if (have) {
         const Segment sg = make_segment_nt(a, tile, lane, 32u);
+        uint32_t* const scr = sc0 + (size_t)cur * a.scratch_words_per_block + lane;
+        uint32_t* const flp = fl0 + (size_t)cur * NBmax * 32 + lane;
 
-        uint32_t cnt = 0, NB = 0;
         if (sg.nvalid) {
             uint32_t fw = misc[1], rc = misc[2];
             // ---- prologue: k-1 bases, one at a time (leaving base = virtual 'A') -------------
@@ -306,97 +316,134 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     if (!SYNC && sg.first_always && e_lo >= eb && e_lo < eb + W) bf |= 1u << (e_lo - eb);
                     bf &= mhi & ~mlo;
                 }
-                sp[0] = bf;
+                flp[b * 32] = bf;
 #pragma unroll
-                for (int q = 0; q < WQ; q++) sp[(1 + q) * 32] = accL[q];
-                sp += ROWS * 32;
+                for (int q = 0; q < WQ; q++) sp[q * 32] = accL[q];
+                sp += WQ * 32;
                 cnt += __popc(bf);
             }
         }
-        // ---- ordered emission, warp-autonomous (no block barriers) ---------------------------
+        // publish this tile's count (aggregate) right away; its prefix is resolved one tile later
         __syncwarp();
-        uint32_t inc = cnt;
+        inc = cnt;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o);
             if (lane >= (uint32_t)o) inc += v;
         }
-        const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-        const unsigned long long gbase = lookback_warp0(a.tile_state, tile, total);
-        if (lane == 0 && tile == a.num_tiles - 1) *a.count_out = gbase + total;
+        if (lane == 31) st_state(a.tile_state + tile, ((unsigned long long)inc << 2) | 1ull);
+        }  // have
+
+        // ---- ordered emission of the PREVIOUS tile, warp-autonomous (no block barriers) --------
+        if (p_valid) {
+        const uint32_t tile_e = p_tile, cnt_e = p_cnt, NB_e = p_NB, inc_e = p_inc;
+        (void)NB_e;
+        const uint32_t* const scr0 = sc0 + (size_t)(cur ^ 1u) * a.scratch_words_per_block;
+        const uint32_t* const flr = fl0 + (size_t)(cur ^ 1u) * NBmax * 32 + lane;
+        const uint32_t total = __shfl_sync(0xffffffffu, inc_e, 31);
+        const uint32_t toff = inc_e - cnt_e;
+        const unsigned long long gbase = lookback_excl(a.tile_state, tile_e, total);
+        if (lane == 0 && tile_e == a.num_tiles - 1) *a.count_out = gbase + total;
         const bool ovf = gbase + total > a.cap;
         if (ovf && lane == 0) *a.overflow = 1u;
         if (a.n_reads != 0) {
-            const uint64_t r = (uint64_t)tile * 32u + lane;
+            const uint64_t r = (uint64_t)tile_e * 32u + lane;
             if (r < a.n_reads) {
-                a.out_offsets[r + 1] = gbase + inc;
+                a.out_offsets[r + 1] = gbase + inc_e;
                 if (r == 0) a.out_offsets[0] = 0;
             }
         }
-        if (ovf || total == 0) continue;
+        if (!ovf && total != 0) {
 
-        uint32_t NBw = NB;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) NBw = max(NBw, __shfl_xor_sync(0xffffffffu, NBw, o));
+        // Tile-uniform addressing (32-bit offsets from the tile's first thread).
         const bool canon_val = a.val_canonical != 0;
-        const uint64_t j00 = a.wbeg + (uint64_t)tile * 32u * a.S;  // first window of the tile
-        unsigned long long cursor = gbase;
-        const uint32_t nitems = 32u * NBw;
-        // items = (owner lane t, van-Herk block b) in output order; 32 flag words per round
-        for (uint32_t i0 = 0; i0 < nitems; i0 += 32) {
-            const uint32_t i = i0 + lane, t = i / NBw, b = i - t * NBw;
-            const uint32_t nb_t = __shfl_sync(0xffffffffu, NB, t);
-            uint32_t f = b < nb_t ? __ldcg(scr0 + (size_t)(b * ROWS) * 32 + t) : 0u;
-            const uint32_t pc = __popc(f);
-            uint32_t pin = pc;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(0xffffffffu, pin, o);
-                if (lane >= (uint32_t)o) pin += v;
-            }
-            const uint32_t tot = __shfl_sync(0xffffffffu, pin, 31);
-            if (tot == 0) continue;
-            uint32_t o = pin - pc;
-            while (f) {
+        const uint64_t j00 = a.wbeg + (uint64_t)tile_e * 32u * a.S;  // first window of the tile
+        const uint32_t hp0 = (a.n_reads == 0 && j00 > 0 && minim) ? 1u : 0u;
+        const uint64_t tbit0 = (uint64_t)((int64_t)(2 * (j00 - hp0)) + a.bitbias);  // lane 0's bit0
+        const uint32_t* const twbase = a.seq + (tbit0 >> 5);
+        const uint32_t tsh = (uint32_t)tbit0 & 31u;
+        const uint64_t trem = a.seq_nwords - 1 - (tbit0 >> 5);
+        const uint32_t twlim = trem > 0x7ffffff0ull ? 0x7ffffff0u : (uint32_t)trem;
+        const bool tclamp = ((tsh + 2u * (32u * a.S + a.l + 64u)) >> 5) + 3u > twlim;
+        const uint32_t pos00 = (uint32_t)j00;
+
+        // Every lane walks its own flag words (coalesced across lanes) and stages its entries at
+        // [toff, toff + cnt) of the tile's output range; FAST_LIST entries per pass.
+        uint32_t bq = 0, produced = 0;
+        uint32_t f = (cnt_e != 0) ? flr[0] : 0u;
+        for (uint32_t cbase = 0; cbase < total; cbase += FAST_LIST) {
+            while (produced < cnt_e && toff + produced < cbase + FAST_LIST) {
+                while (f == 0) {
+                    bq++;
+                    f = flr[bq * 32];
+                }
                 const uint32_t bit = (uint32_t)__ffs(f) - 1u;
                 f &= f - 1u;
-                list[o++] = (t << 16) | (b * W + bit);
+                list[toff + produced - cbase] = (lane << 16) | (bq * W + bit);
+                produced++;
             }
             __syncwarp();
-            for (uint32_t x = lane; x < tot; x += 32) {
+            const uint32_t nent = min(FAST_LIST, total - cbase);
+            uint32_t* const opos = a.pos + (gbase + cbase);
+            for (uint32_t x = lane; x < nent; x += 32) {
                 const uint32_t dsc = list[x];
                 const uint32_t t2 = dsc >> 16, e = dsc & 0xffffu, b2 = e / W, bit2 = e - b2 * W;
-                const uint32_t wv = __ldcg(scr0 + (size_t)(b2 * ROWS + 1 + (bit2 >> 2)) * 32 + t2);
+                const uint32_t wv = __ldcg(scr0 + (size_t)(b2 * WQ + (bit2 >> 2)) * 32 + t2);
                 const uint32_t lowb = (wv >> (8u * (bit2 & 3u))) & 0xffu;
                 const uint32_t jl = e - (W - 1);  // local window index of the owner
-                uint64_t pos_base, win_base, bit0;
-                uint32_t hp;
-                if (a.n_reads == 0) {
-                    const uint64_t j0 = j00 + (uint64_t)t2 * a.S;
-                    hp = (j0 > 0 && minim) ? 1u : 0u;
-                    pos_base = j0 - hp;
-                    win_base = j0;
-                    bit0 = (uint64_t)((int64_t)(2 * pos_base) + a.bitbias);
-                } else {
-                    const Segment og = make_segment_nt(a, tile, t2, 32u);
-                    hp = 0, pos_base = 0, win_base = 0, bit0 = og.bit0;
-                }
-                const uint32_t jv = jl - hp;
                 const uint32_t local = minim ? jl + ((lowb - jl) & 0xffu) : jl;
-                const unsigned long long oi = cursor + x;
-                a.pos[oi] = (uint32_t)(pos_base + local);
-                if (a.want_sk) a.sk[oi] = (uint32_t)(win_base + jv);
-                if (a.value_bits == 64) {
-                    a.val[oi] = kmer_value_u64(a, bit0 + 2ull * local, a.val_len, canon_val);
-                } else if (a.value_bits == 128) {
-                    uint64_t lo, hi;
-                    kmer_value_u128(a, bit0 + 2ull * local, a.val_len, canon_val, lo, hi);
-                    reinterpret_cast<ulonglong2*>(a.val)[oi] = make_ulonglong2(lo, hi);
+                if (a.n_reads == 0) {
+                    // owner's local base 0 = tile base + t2*S (- has_prev, which only differs for
+                    // the very first thread of the sequence)
+                    const uint32_t hp = (minim && !(j00 == 0 && t2 == 0)) ? 1u : 0u;
+                    const uint32_t rel = t2 * a.S - hp + hp0 + local;  // bases from the tile's bit0
+                    opos[x] = pos00 - hp0 + rel;
+                    if (a.want_sk) a.sk[gbase + cbase + x] = pos00 + t2 * a.S + (jl - hp);
+                    if (a.value_bits == 64) {
+                        const uint32_t pbit = tsh + 2u * rel, wl = pbit >> 5, sh = pbit & 31u;
+                        uint32_t w0, w1, w2;
+                        if (!tclamp) {
+                            const uint32_t* pw = twbase + wl;
+                            w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2);
+                        } else {
+                            w0 = __ldg(twbase + min(wl, twlim)), w1 = __ldg(twbase + min(wl + 1, twlim));
+                            w2 = __ldg(twbase + min(wl + 2, twlim));
+                        }
+                        const uint32_t vlo = __funnelshift_r(w0, w1, sh), vhi = __funnelshift_r(w1, w2, sh);
+                        uint64_t v = (uint64_t)vlo | ((uint64_t)vhi << 32);
+                        const uint32_t len = a.val_len;
+                        if (len < 32) v &= (1ull << (2 * len)) - 1ull;
+                        if (canon_val) {
+                            const uint64_t r = (swap_pairs64(__brevll(v)) ^ 0xAAAAAAAAAAAAAAAAull) >> (64 - 2 * len);
+                            v = r < v ? r : v;
+                        }
+                        a.val[gbase + cbase + x] = v;
+                    } else if (a.value_bits == 128) {
+                        uint64_t lo, hi;
+                        kmer_value_u128(a, tbit0 + 2ull * rel, a.val_len, canon_val, lo, hi);
+                        reinterpret_cast<ulonglong2*>(a.val)[gbase + cbase + x] = make_ulonglong2(lo, hi);
+                    }
+                } else {
+                    const Segment og = make_segment_nt(a, tile_e, t2, 32u);
+                    const unsigned long long oi = gbase + cbase + x;
+                    a.pos[oi] = local;
+                    if (a.want_sk) a.sk[oi] = jl;
+                    if (a.value_bits == 64) {
+                        a.val[oi] = kmer_value_u64(a, og.bit0 + 2ull * local, a.val_len, canon_val);
+                    } else if (a.value_bits == 128) {
+                        uint64_t lo, hi;
+                        kmer_value_u128(a, og.bit0 + 2ull * local, a.val_len, canon_val, lo, hi);
+                        reinterpret_cast<ulonglong2*>(a.val)[oi] = make_ulonglong2(lo, hi);
+                    }
                 }
             }
-            cursor += tot;
             __syncwarp();
         }
+        }  // !ovf && total
+        }  // p_valid
+        if (!have) break;
+        p_valid = 1, p_tile = tile, p_cnt = cnt, p_NB = NB, p_inc = inc;
+        cur ^= 1u;
     }
 }
 
@@ -420,9 +467,11 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     } else {
         // long segments amortise the (k+w-2)-base warm-up; keep >= ~3 tiles per resident block
         uint64_t want = nwin / (slots * 3 * 32);
-        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 1024);
+        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 256);
     }
     s = std::max<uint32_t>(16, (s + 15) / 16 * 16);
+    // flag words live in shared memory (one per W windows): keep ~4 blocks per SM resident
+    while (s > 16 && fast_smem(s, p.w) > 56 * 1024) s -= 16;
     if ((uint64_t)s + p.w + 2 >= 65535) return false;
     const uint64_t Tt = (uint64_t)32 * s;
     const uint64_t tiles = (nwin + Tt - 1) / Tt;
@@ -437,7 +486,11 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
 template <int W, bool HC, bool LR, bool SYNC>
 inline int launch_fast_inst(uint32_t grid, const KArgs& a, cudaStream_t st) {
     auto kern = mz_fast_kernel<W, HC, LR, SYNC>;
-    kern<<<grid, FAST_NT, FAST_SMEM, st>>>(a);
+    const size_t smem = fast_smem(a.S, W);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        return MZ_ERR_CUDA;
+    kern<<<grid, FAST_NT, smem, st>>>(a);
     return cudaGetLastError() == cudaSuccess ? MZ_OK : MZ_ERR_CUDA;
 }
 
