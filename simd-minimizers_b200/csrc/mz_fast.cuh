@@ -385,13 +385,24 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             __syncwarp();
             const uint32_t nent = min(FAST_LIST, total - cbase);
             uint32_t* const opos = a.pos + (gbase + cbase);
+            // sweep 1: fetch each entry's position byte from the L2 scratch (independent loads,
+            // unrolled so several are in flight) and fold it into the staged descriptor
+#pragma unroll 4
             for (uint32_t x = lane; x < nent; x += 32) {
                 const uint32_t dsc = list[x];
                 const uint32_t t2 = dsc >> 16, e = dsc & 0xffffu, b2 = e / W, bit2 = e - b2 * W;
                 const uint32_t wv = __ldcg(scr0 + (size_t)(b2 * WQ + (bit2 >> 2)) * 32 + t2);
                 const uint32_t lowb = (wv >> (8u * (bit2 & 3u))) & 0xffu;
                 const uint32_t jl = e - (W - 1);  // local window index of the owner
-                const uint32_t local = minim ? jl + ((lowb - jl) & 0xffu) : jl;
+                list[x] = (t2 << 27) | (((lowb - jl) & 0xffu) << 16) | jl;
+            }
+            __syncwarp();
+            // sweep 2: positions, super-k-mer starts and k-mer values, coalesced stores
+#pragma unroll 2
+            for (uint32_t x = lane; x < nent; x += 32) {
+                const uint32_t dsc = list[x];
+                const uint32_t t2 = dsc >> 27, jl = dsc & 0xffffu;
+                const uint32_t local = minim ? jl + ((dsc >> 16) & 0xffu) : jl;
                 if (a.n_reads == 0) {
                     // owner's local base 0 = tile base + t2*S (- has_prev, which only differs for
                     // the very first thread of the sequence)
