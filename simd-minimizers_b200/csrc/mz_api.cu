@@ -4,6 +4,8 @@
 #include "../../include/mz_b200.h"
 
 #include <algorithm>
+#include <chrono>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -82,9 +84,13 @@ struct DevState {
 
 }  // namespace
 
+constexpr int kSlots = 3;  // chunks in flight per device in the pipelined host path
+
 struct mz_ctx {
-    std::vector<DevState> devs;
+    std::vector<DevState> devs;                 // slot 0 of every device
+    std::vector<std::vector<DevState>> extra;   // slots 1..kSlots-1 of every device
     mz_timing timing{};
+    DevState& slot(size_t dev, int s) { return s == 0 ? devs[dev] : extra[dev][s - 1]; }
 };
 
 namespace {
@@ -214,12 +220,130 @@ uint64_t estimate_capacity(const mz_params& p, uint64_t nwin) {
     return (uint64_t)std::min<double>(est, (double)nwin);
 }
 
+cudaError_t init_devstate(DevState& d, int device) {
+    d.device = device;
+    cudaError_t e = cudaSetDevice(device);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable);
+    int v = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+    d.sm_count = v;
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    d.smem_optin = (size_t)v;
+    return e;
+}
+
 int check_values(const mz_params& p) {
     if (p.value_bits == 0) return MZ_OK;
     if (p.value_bits != 64 && p.value_bits != 128) return MZ_ERR_BAD_ARG;
     uint32_t len = p.mode == MZ_MODE_MINIMIZER ? p.k : p.k + p.w - 1;
     if (len > p.value_bits / 2) return MZ_ERR_VALUE_WIDTH;
     return MZ_OK;
+}
+
+// Fill the kernel arguments that describe a device copy of bases [blo, ...) of the sequence.
+void fill_input_args(mz::KArgs& a, const mz_params& p, const uint8_t* d_in, uint64_t bp_offset,
+                     uint64_t byte_lo, size_t nbytes, uint64_t nwin) {
+    fill_hash_args(a, p);
+    a.seq = reinterpret_cast<const uint32_t*>(d_in);
+    a.bitbias = (int64_t)(2 * bp_offset) - (int64_t)(8 * byte_lo);
+    a.seq_nwords = (nbytes + 3) / 4;
+    a.nwin = nwin;
+}
+
+// Single device, large input: windows are cut into chunks that flow through kSlots streams so
+// that the H2D copy of chunk c+2, the kernel of chunk c+1 and the D2H copy of chunk c overlap.
+// Chunks are seams like any other shard (one extra window on the left); outputs land in the
+// caller's arrays in order.
+int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64_t bp_offset,
+                  uint64_t n_bp, mz_out* out) {
+    const uint32_t l = p.k + p.w - 1;
+    const uint64_t nwin = n_bp - l + 1;
+    const uint32_t vw = p.value_bits / 64;
+    uint64_t chunk = std::max<uint64_t>(1ull << 25, (nwin + 23) / 24);
+    const char* env = getenv("MZ_CHUNK_WINDOWS");
+    if (env) chunk = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
+    const uint64_t nchunks = (nwin + chunk - 1) / chunk;
+    struct Job {
+        uint64_t wb, we, cap, byte_lo;
+        size_t nbytes;
+    };
+    std::vector<Job> jobs(nchunks);
+    uint64_t total = 0;
+    bool too_small = false;
+    int rc;
+    CK(cudaSetDevice(ctx->devs[0].device));
+
+    auto issue = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        Job& j = jobs[c];
+        j.wb = c * chunk;
+        j.we = std::min<uint64_t>(j.wb + chunk, nwin);
+        j.cap = estimate_capacity(p, j.we - j.wb);
+        const uint64_t blo = j.wb > 0 ? j.wb - 1 : 0;
+        j.byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
+        j.nbytes = (bp_offset + j.we + l - 1 + 3) / 4 - j.byte_lo;
+        int r;
+        if ((r = d.in.reserve(j.nbytes + 64))) return r;
+        if ((r = d.pos.reserve(j.cap))) return r;
+        if (p.want_sk && (r = d.sk.reserve(j.cap))) return r;
+        if (vw && (r = d.val.reserve(j.cap * vw))) return r;
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        CK(cudaMemcpyAsync(d.in.p, packed + j.byte_lo, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaEventRecord(d.ev[1], d.stream));
+        mz::KArgs a{};
+        fill_input_args(a, p, d.in.p, bp_offset, j.byte_lo, j.nbytes, nwin);
+        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
+        if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
+        CK(cudaEventRecord(d.ev[2], d.stream));
+        return MZ_OK;
+    };
+    auto retire = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        Job& j = jobs[c];
+        CK(cudaStreamSynchronize(d.stream));
+        float h2d = 0, ker = 0;
+        cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
+        cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
+        ctx->timing.h2d_ms += h2d;
+        ctx->timing.kernel_ms += ker;
+        uint64_t count = d.hs->count;
+        if (d.hs->overflow) {  // capacity estimate too small: redo this chunk with the exact size
+            int r;
+            j.cap = count;
+            if ((r = d.pos.reserve(j.cap))) return r;
+            if (p.want_sk && (r = d.sk.reserve(j.cap))) return r;
+            if (vw && (r = d.val.reserve(j.cap * vw))) return r;
+            mz::KArgs a{};
+            fill_input_args(a, p, d.in.p, bp_offset, j.byte_lo, j.nbytes, nwin);
+            a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
+            if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
+            CK(cudaStreamSynchronize(d.stream));
+            if (d.hs->overflow) {
+                g_last_error = "internal: exact-capacity re-run overflowed";
+                return MZ_ERR_CUDA;
+            }
+            count = d.hs->count;
+        }
+        if (total + count > out->capacity) too_small = true;
+        if (!too_small && count) {
+            CK(cudaMemcpyAsync(out->pos + total, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (p.want_sk) CK(cudaMemcpyAsync(out->sk + total, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (vw) CK(cudaMemcpyAsync(out->val + total * vw, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+        }
+        total += count;
+        return MZ_OK;
+    };
+    for (uint64_t c = 0; c < nchunks; c++) {
+        if ((rc = issue(c))) return rc;
+        if (c + 1 >= (uint64_t)kSlots && (rc = retire(c + 1 - kSlots))) return rc;
+    }
+    for (uint64_t c = nchunks >= (uint64_t)kSlots ? nchunks - (kSlots - 1) : 0; c < nchunks; c++)
+        if ((rc = retire(c))) return rc;
+    for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(ctx->slot(0, sl).stream));
+    out->count = total;
+    return too_small ? MZ_ERR_CAPACITY : MZ_OK;
 }
 
 }  // namespace
@@ -331,22 +455,16 @@ int mz_ctx_create(const int* device_ids, int n_devices, mz_ctx** out) {
     }
     mz_ctx* ctx = new mz_ctx();
     ctx->devs.resize(ids.size());
+    ctx->extra.resize(ids.size());
     for (size_t i = 0; i < ids.size(); i++) {
-        DevState& d = ctx->devs[i];
-        d.device = ids[i];
-        cudaError_t e = cudaSetDevice(d.device);
-        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-        for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
-        if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable);
-        int v = 0;
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d.device);
-        d.sm_count = v;
-        if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, d.device);
-        d.smem_optin = (size_t)v;
-        if (e != cudaSuccess) {
-            int code = cuda_fail(e, "context setup", __LINE__);
-            mz_ctx_destroy(ctx);
-            return code;
+        ctx->extra[i].resize(kSlots - 1);
+        for (int sl = 0; sl < kSlots; sl++) {
+            cudaError_t e = init_devstate(ctx->slot(i, sl), ids[i]);
+            if (e != cudaSuccess) {
+                int code = cuda_fail(e, "context setup", __LINE__);
+                mz_ctx_destroy(ctx);
+                return code;
+            }
         }
     }
     *out = ctx;
@@ -355,7 +473,12 @@ int mz_ctx_create(const int* device_ids, int n_devices, mz_ctx** out) {
 
 void mz_ctx_destroy(mz_ctx* ctx) {
     if (!ctx) return;
-    for (DevState& d : ctx->devs) {
+    std::vector<DevState*> all;
+    for (DevState& d : ctx->devs) all.push_back(&d);
+    for (auto& v : ctx->extra)
+        for (DevState& d : v) all.push_back(&d);
+    for (DevState* dp : all) {
+        DevState& d = *dp;
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.scratch.release(), d.rows.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
@@ -441,6 +564,14 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
     const size_t ndev = std::min<uint64_t>(ctx->devs.size(), nwin);
     const uint32_t vw = p->value_bits / 64;  // u64 words per value
     ctx->timing = mz_timing{};
+    uint64_t pipe_min = 1ull << 26;
+    if (const char* e = getenv("MZ_PIPELINE_MIN_WINDOWS")) pipe_min = strtoull(e, nullptr, 10);
+    if (ndev == 1 && nwin >= pipe_min && !getenv("MZ_NO_PIPELINE")) {
+        const auto t0 = std::chrono::steady_clock::now();
+        rc = run_pipelined(ctx, *p, packed, bp_offset, n_bp, out);
+        ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        return rc;
+    }
 
     struct Shard {
         uint64_t wb, we, cap, count;

@@ -228,3 +228,15 @@ def test_device_resident_and_window_ranges(sm, oracle):
     p.want_sk, p.value_bits = 0, 0
     rc = L.mz_run_device(ctx.handle, 0, C.byref(p), d_in.data_ptr(), 1, n, 0, 0, C.byref(out))
     assert rc == 8 and out.count == len(epos)
+
+
+def test_pipelined_host_path_chunk_seams(sm, oracle, monkeypatch):
+    """mz_run's chunk-pipelined path (H2D / kernel / D2H overlap): force tiny chunks so many
+    chunk seams fall inside the sequence; result must equal the single-shot run."""
+    monkeypatch.setenv("MZ_PIPELINE_MIN_WINDOWS", "1")
+    n = 400_000
+    packed = oracle.synth_packed(17, n + 2)
+    for chunk in ("777", "65536", "100000"):
+        monkeypatch.setenv("MZ_CHUNK_WINDOWS", chunk)
+        for (k, w, c, mode) in ((31, 19, True, 0), (21, 11, False, 0), (31, 11, True, 1), (9, 5, False, 2), (40, 40, False, 0)):
+            _check_case(sm, oracle, packed, 2, n, k, w, c, mode)
