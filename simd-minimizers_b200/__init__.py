@@ -373,6 +373,54 @@ class Builder:
         self.run(seq, v)
         return v.array
 
+    def run_batch(self, packed: np.ndarray, *, starts=None, lens=None, stride_bytes: int = 0,
+                  read_len: int = 0, n_reads: int | None = None, value_bits: int | None = None):
+        """Many independent reads in one launch (mz_run_batch).  Equivalent to the reference
+        idiom ``for s in &seqs { v.clear(); builder.run(s, &mut v) }``
+        (bench/src/bin/paper.rs:98-105) with the per-read results returned as CSR:
+        ``offsets[r]:offsets[r+1]`` index ``pos`` / ``sk`` / ``vals``; positions are relative to
+        the read start.  Either ``starts``+``lens`` (bases, arbitrary layout) or a fixed
+        ``stride_bytes`` + ``read_len`` layout."""
+        assert packed.dtype == np.uint8 and packed.flags.c_contiguous
+        length = self.k if self.syncmer == 0 else self.k + self.w - 1
+        if value_bits is None:
+            value_bits = 64 if length <= 32 else 0
+        p = self._params(value_bits)
+        L = _ffi.lib()
+        l = self.k + self.w - 1
+        if starts is not None:
+            starts = np.ascontiguousarray(starts, dtype=np.uint64)
+            lens = np.ascontiguousarray(lens, dtype=np.uint32)
+            n_reads = int(starts.size)
+            nwin = int(np.maximum(lens.astype(np.int64) - l + 1, 0).sum())
+        else:
+            assert n_reads is not None
+            nwin = max(0, read_len - l + 1) * n_reads
+        _check(L.mz_params_validate(C.byref(p), int(lens.max()) if starts is not None and n_reads else read_len))
+        dens = 2.0 / (self.w + 1) if self.syncmer == 0 else (2.0 / self.w if self.syncmer == 1 else 1.0 / self.w)
+        cap = int(min(nwin, nwin * dens * 1.25 + n_reads + 4096))
+        ctx = self._ctx or default_context()
+        vw = value_bits // 64
+        offsets = np.zeros(n_reads + 1, dtype=np.uint64)
+        while True:
+            pos = np.empty(max(cap, 1), dtype=np.uint32)
+            sk = np.empty(max(cap, 1), dtype=np.uint32) if p.want_sk else None
+            val = np.empty(max(cap, 1) * max(vw, 1), dtype=np.uint64) if vw else None
+            out = MzOut(pos.ctypes.data, sk.ctypes.data if sk is not None else None,
+                        val.ctypes.data if val is not None else None, cap, 0)
+            rc = L.mz_run_batch(ctx.handle, C.byref(p), packed.ctypes.data, packed.size, n_reads,
+                                starts.ctypes.data if starts is not None else None,
+                                lens.ctypes.data if starts is not None else None,
+                                stride_bytes, read_len, offsets.ctypes.data, C.byref(out))
+            if rc == _ffi.MZ_ERR_CAPACITY:
+                cap = int(out.count)
+                continue
+            _check(rc)
+            break
+        m = int(out.count)
+        vals = None if not vw else (val[:m] if vw == 1 else val[:2 * m].reshape(m, 2))
+        return offsets, pos[:m], (sk[:m] if sk is not None else None), vals
+
 
 def minimizers(k: int, w: int) -> Builder:                  # src/lib.rs:240
     return Builder(k, w, False, 0)

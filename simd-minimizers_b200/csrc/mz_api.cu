@@ -686,9 +686,147 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
 int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t packed_bytes,
                  uint64_t n_reads, const uint64_t* read_start_bp, const uint32_t* read_len_bp,
                  uint64_t stride_bytes, uint32_t fixed_len_bp, uint64_t* out_offsets, mz_out* out) {
-    (void)ctx, (void)p, (void)packed, (void)packed_bytes, (void)n_reads, (void)read_start_bp;
-    (void)read_len_bp, (void)stride_bytes, (void)fixed_len_bp, (void)out_offsets, (void)out;
-    return MZ_ERR_UNSUPPORTED;  // TODO(batch)
+    if (!ctx || !p || !out || !out_offsets) return MZ_ERR_BAD_ARG;
+    if ((read_start_bp == nullptr) != (read_len_bp == nullptr)) return MZ_ERR_BAD_ARG;
+    out->count = 0;
+    out_offsets[0] = 0;
+    if (n_reads == 0) return MZ_OK;
+    const uint32_t l = p->k + p->w - 1;
+    uint32_t max_len = fixed_len_bp;
+    uint64_t total_windows = 0;
+    if (read_len_bp) {
+        max_len = 0;
+        for (uint64_t r = 0; r < n_reads; r++) {
+            max_len = std::max(max_len, read_len_bp[r]);
+            total_windows += read_len_bp[r] >= l ? read_len_bp[r] - l + 1 : 0;
+            if (2 * (read_start_bp[r] + read_len_bp[r]) > 8 * packed_bytes) return MZ_ERR_BAD_ARG;
+        }
+    } else {
+        if (stride_bytes == 0 || (fixed_len_bp + 3) / 4 > stride_bytes) return MZ_ERR_BAD_ARG;
+        if ((n_reads - 1) * stride_bytes + (fixed_len_bp + 3) / 4 > packed_bytes) return MZ_ERR_BAD_ARG;
+        total_windows = fixed_len_bp >= l ? (uint64_t)(fixed_len_bp - l + 1) * n_reads : 0;
+    }
+    int rc = mz_params_validate(p, max_len);
+    if (rc) return rc;
+    if (total_windows == 0) {
+        for (uint64_t r = 0; r <= n_reads; r++) out_offsets[r] = 0;
+        return MZ_OK;
+    }
+    if (!packed || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
+    const uint32_t S = max_len - l + 1;  // windows of the longest read: one read per thread
+    const uint32_t vw = p->value_bits / 64;
+    DevState& d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    ctx->timing = mz_timing{};
+
+    // geometry: fast kernel (tile = 32 reads) when the per-thread record fits, else generic
+    Plan pl;
+    mz::FastPlan fp;
+    bool fast = p->w <= mz::FAST_MAX_W && !(p->hash_canonical && !p->strand_tiebreak) &&
+                mz::fast_smem(S, p->w) <= 56 * 1024 && (uint64_t)S + p->w + 2 < 65535;
+    if (fast) {
+        const uint64_t tiles = (n_reads + 31) / 32;
+        if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
+        fp.S = S;
+        fp.num_tiles = (uint32_t)tiles;
+        fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * 4);
+        fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
+        pl.num_tiles = fp.num_tiles;
+    } else {
+        const bool lr = p->strand_tiebreak != 0;
+        uint32_t NT = 128;
+        const size_t budget = std::min<size_t>(d.smem_optin, 200 * 1024);
+        while (NT >= 32 && generic_smem(NT, S, p->w, lr) > budget) NT /= 2;
+        if (NT < 32 || (uint64_t)S + p->w + 2 >= 65535) {
+            g_last_error = "mz_run_batch: reads too long for the one-read-per-thread batch kernels";
+            return MZ_ERR_UNSUPPORTED;
+        }
+        const uint64_t tiles = (n_reads + NT - 1) / NT;
+        if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
+        pl.NT = NT;
+        pl.S = S;
+        pl.smem = generic_smem(NT, S, p->w, lr);
+        pl.num_tiles = (uint32_t)tiles;
+    }
+
+    uint64_t cap = std::min<uint64_t>(estimate_capacity(*p, total_windows) + n_reads, total_windows);
+    if ((rc = d.in.reserve(packed_bytes + 64))) return rc;
+    if ((rc = d.offs.reserve(n_reads + 1))) return rc;
+    if (read_start_bp) {
+        if ((rc = d.rstart.reserve(n_reads))) return rc;
+        if ((rc = d.rlen.reserve(n_reads))) return rc;
+    }
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    CK(cudaMemcpyAsync(d.in.p, packed, packed_bytes, cudaMemcpyHostToDevice, d.stream));
+    if (read_start_bp) {
+        CK(cudaMemcpyAsync(d.rstart.p, read_start_bp, n_reads * 8, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d.rlen.p, read_len_bp, n_reads * 4, cudaMemcpyHostToDevice, d.stream));
+    }
+    CK(cudaEventRecord(d.ev[1], d.stream));
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = d.pos.reserve(cap))) return rc;
+        if (p->want_sk && (rc = d.sk.reserve(cap))) return rc;
+        if (vw && (rc = d.val.reserve(cap * vw))) return rc;
+        if ((rc = d.scratch.reserve(2 + (size_t)pl.num_tiles))) return rc;
+        CK(cudaMemsetAsync(d.scratch.p, 0, (2 + (size_t)pl.num_tiles) * sizeof(unsigned long long), d.stream));
+        mz::KArgs a{};
+        fill_hash_args(a, *p);
+        a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
+        a.bitbias = 0;
+        a.seq_nwords = (packed_bytes + 3) / 4;
+        a.nwin = total_windows;
+        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = cap;
+        a.S = S;
+        a.num_tiles = pl.num_tiles;
+        a.count_out = d.scratch.p;
+        a.ticket = reinterpret_cast<uint32_t*>(d.scratch.p + 1);
+        a.overflow = a.ticket + 1;
+        a.tile_state = d.scratch.p + 2;
+        a.n_reads = n_reads;
+        a.read_start_bp = read_start_bp ? d.rstart.p : nullptr;
+        a.read_len_bp = read_start_bp ? d.rlen.p : nullptr;
+        a.stride_bits = stride_bytes * 8;
+        a.fixed_len_bp = fixed_len_bp;
+        a.out_offsets = d.offs.p;
+        if (fast) {
+            if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS * 2))) return rc;
+            a.scratch = d.rows.p;
+            a.scratch_words_per_block = fp.scratch_words_per_block;
+            rc = mz::launch_fast(*p, fp.grid, a, d.stream);
+        } else {
+            rc = launch_generic(*p, pl, a, d.stream);
+        }
+        if (rc) {
+            if (rc == MZ_ERR_CUDA && g_last_error.empty()) g_last_error = "kernel launch failed";
+            return rc;
+        }
+        ctx->timing.kernel_launches++;
+        CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
+        CK(cudaEventRecord(d.ev[2], d.stream));
+        CK(cudaStreamSynchronize(d.stream));
+        if (!d.hs->overflow) break;
+        if (attempt == 1) {
+            g_last_error = "internal: exact-capacity re-run overflowed";
+            return MZ_ERR_CUDA;
+        }
+        cap = d.hs->count;
+    }
+    const uint64_t count = d.hs->count;
+    out->count = count;
+    if (count > out->capacity) return MZ_ERR_CAPACITY;
+    CK(cudaMemcpyAsync(out_offsets, d.offs.p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+    if (count) {
+        CK(cudaMemcpyAsync(out->pos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (p->want_sk) CK(cudaMemcpyAsync(out->sk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (vw) CK(cudaMemcpyAsync(out->val, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+    }
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, d.ev[0], d.ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, d.ev[1], d.ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, d.ev[2], d.ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, d.ev[0], d.ev[3]);
+    return MZ_OK;
 }
 
 }  // extern "C"

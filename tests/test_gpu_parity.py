@@ -240,3 +240,63 @@ def test_pipelined_host_path_chunk_seams(sm, oracle, monkeypatch):
         monkeypatch.setenv("MZ_CHUNK_WINDOWS", chunk)
         for (k, w, c, mode) in ((31, 19, True, 0), (21, 11, False, 0), (31, 11, True, 1), (9, 5, False, 2), (40, 40, False, 0)):
             _check_case(sm, oracle, packed, 2, n, k, w, c, mode)
+
+
+def _oracle_batch(oracle, packed, starts, lens, k, w, canonical, mode, want_sk):
+    pr = oracle.make_params(k, w, canonical=canonical, mode=mode)
+    offs, pos, sks, vals = [0], [], [], []
+    length = k if mode == 0 else k + w - 1
+    for s, n in zip(starts, lens):
+        p, sk = oracle.run(packed, int(s), int(n), pr, want_sk=want_sk)
+        pos.append(p)
+        if want_sk:
+            sks.append(sk)
+        if length <= 32:
+            vals.append(oracle.values_u64(packed, int(s), length, canonical, p))
+        offs.append(offs[-1] + len(p))
+    cat = lambda xs, dt: np.concatenate(xs) if xs else np.zeros(0, dt)
+    return (np.array(offs, dtype=np.uint64), cat(pos, np.uint32), cat(sks, np.uint32) if want_sk else None,
+            cat(vals, np.uint64) if length <= 32 else None)
+
+
+def test_batch_fixed_stride_short_reads(sm, oracle):
+    """BASELINE config 5 shape: 150 bp reads at a 38-byte stride, canonical k=21 w=11; every
+    read must give exactly what a per-read call gives (bench/src/bin/paper.rs:98-105)."""
+    n_reads, read_len, stride = 5000, 150, 38
+    packed = oracle.synth_packed(31, n_reads * stride * 4 + 64)
+    starts = np.arange(n_reads, dtype=np.uint64) * (stride * 4)
+    lens = np.full(n_reads, read_len, dtype=np.uint32)
+    for (k, w, c, mode) in ((21, 11, True, 0), (21, 11, False, 0), (15, 10, False, 1), (31, 5, True, 1)):
+        b = _builder(sm, k, w, c, mode)
+        sk = sm.U32Vec()
+        bb = b.super_kmers(sk) if mode == 0 else b
+        offs, pos, sks, vals = bb.run_batch(packed, stride_bytes=stride, read_len=read_len, n_reads=n_reads)
+        eo, ep, es, ev = _oracle_batch(oracle, packed, starts, lens, k, w, c, mode, mode == 0)
+        assert np.array_equal(offs, eo) and np.array_equal(pos, ep), (k, w, c, mode)
+        if mode == 0:
+            assert np.array_equal(sks, es)
+        if ev is not None:
+            assert np.array_equal(vals, ev)
+
+
+def test_batch_ragged_reads(sm, oracle):
+    """Ragged batch: empty, too-short and unaligned reads, including w > 32 (generic kernel)."""
+    rng = np.random.default_rng(8)
+    n_reads = 700
+    lens = rng.integers(0, 400, n_reads).astype(np.uint32)
+    lens[:5] = [0, 1, 30, 31, 32]
+    gaps = rng.integers(0, 9, n_reads)
+    starts = np.zeros(n_reads, dtype=np.uint64)
+    cur = 3
+    for i in range(n_reads):
+        cur += int(gaps[i])
+        starts[i] = cur
+        cur += int(lens[i])
+    packed = oracle.synth_packed(77, cur + 64)
+    for (k, w, c, mode) in ((21, 11, True, 0), (5, 4, False, 0), (9, 40, False, 0), (11, 33, True, 1), (7, 3, True, 2)):
+        b = _builder(sm, k, w, c, mode)
+        offs, pos, _, vals = b.run_batch(packed, starts=starts, lens=lens)
+        eo, ep, _, ev = _oracle_batch(oracle, packed, starts, lens, k, w, c, mode, False)
+        assert np.array_equal(offs, eo) and np.array_equal(pos, ep), (k, w, c, mode)
+        if ev is not None:
+            assert np.array_equal(vals, ev)
