@@ -1,0 +1,155 @@
+// simd_minimizers.hpp -- header-only C++ mirror of the reference builder API
+// (rust-seq/simd-minimizers v3.0.0, src/lib.rs:225-654) over the C ABI in mz_b200.h.
+//
+//   auto pos  = simd_minimizers::canonical_minimizer_positions(seq, k, w);
+//   std::vector<uint32_t> p, sk;
+//   auto out  = simd_minimizers::canonical_minimizers(k, w).hasher(h).super_kmers(sk).run(seq, p);
+//   auto vals = out.values_u64();
+//
+// The reference's assert!/panic! become std::invalid_argument with the reference's message.
+// Link with -lmzb200.  No CPU fallback: without a CUDA device every run() throws.
+#pragma once
+#include <cstdint>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "mz_b200.h"
+
+namespace simd_minimizers {
+
+// packed_seq::PackedSeq: 4 bases per byte, first base in the low bits, A=0 C=1 T=2 G=3.
+struct PackedSeq {
+    const uint8_t* data = nullptr;
+    uint64_t offset = 0;  // bases into data
+    uint64_t len = 0;     // bases
+    PackedSeq slice(uint64_t b, uint64_t e) const { return {data, offset + b, e - b}; }
+};
+
+struct Hasher {  // seq-hash NtHasher<RC> / MulHasher<RC>
+    enum Kind { Nt, Mul } kind = Nt;
+    uint32_t k = 0;
+    bool canonical = true;
+    static Hasher nt(uint32_t k, bool rc = true) { return {Nt, k, rc}; }
+    static Hasher mul(uint32_t k, bool rc = true) { return {Mul, k, rc}; }
+    bool is_canonical() const { return canonical; }
+};
+
+namespace detail {
+inline void check(int rc) {
+    if (rc == MZ_OK) return;
+    std::string msg = mz_strerror(rc);
+    if (rc == MZ_ERR_CUDA) msg += std::string(": ") + mz_last_error();
+    if (rc >= MZ_ERR_W_RANGE && rc <= MZ_ERR_VALUE_WIDTH) throw std::invalid_argument(msg);
+    throw std::runtime_error(msg);
+}
+inline mz_ctx* thread_ctx() {  // thread_local scratch, like src/lib.rs:217-219
+    struct Holder {
+        mz_ctx* c = nullptr;
+        ~Holder() { mz_ctx_destroy(c); }
+    };
+    thread_local Holder h;
+    if (!h.c) check(mz_ctx_create(nullptr, 0, &h.c));
+    return h.c;
+}
+}  // namespace detail
+
+class Output {
+public:
+    Output(uint32_t len, std::vector<uint64_t> v, const std::vector<uint32_t>* p) : len_(len), vals_(std::move(v)), pos_(p) {}
+    uint32_t len() const { return len_; }  // k for minimizers, k+w-1 for syncmers
+    const std::vector<uint64_t>& values_u64() const {
+        if (len_ > 32) throw std::invalid_argument(mz_strerror(MZ_ERR_VALUE_WIDTH));
+        return vals_;
+    }
+    const std::vector<uint32_t>& positions() const { return *pos_; }
+
+private:
+    uint32_t len_;
+    std::vector<uint64_t> vals_;
+    const std::vector<uint32_t>* pos_;
+};
+
+class Builder {
+public:
+    Builder(uint32_t k, uint32_t w, bool canonical, uint32_t syncmer) : k_(k), w_(w), canonical_(canonical), syncmer_(syncmer) {}
+    Builder hasher(const Hasher& h) const {
+        if (sk_) throw std::logic_error("hasher() must be called before super_kmers()");  // src/lib.rs:323-338
+        Builder b = *this;
+        b.hasher_ = h;
+        b.has_hasher_ = true;
+        return b;
+    }
+    Builder super_kmers(std::vector<uint32_t>& sk) const {
+        if (syncmer_) throw std::logic_error("super_kmers() is only available for minimizers");  // src/lib.rs:339
+        Builder b = *this;
+        b.sk_ = &sk;
+        return b;
+    }
+    // Appends to min_pos (and to the super-k-mer vector), src/lib.rs:80-81.
+    Output run(const PackedSeq& seq, std::vector<uint32_t>& min_pos) const {
+        mz_params p;
+        detail::check(mz_params_nthash(&p, k_, w_, syncmer_, canonical_));
+        if (has_hasher_) {
+            if (hasher_.k != k_) throw std::invalid_argument("hasher.k() must equal k");
+            detail::check(hasher_.kind == Hasher::Nt ? mz_params_set_nthash(&p, hasher_.canonical)
+                                                    : mz_params_set_mulhash(&p, hasher_.canonical));
+        }
+        const uint32_t len = syncmer_ ? k_ + w_ - 1 : k_;
+        p.want_sk = sk_ != nullptr;
+        p.value_bits = len <= 32 ? 64 : 0;
+        detail::check(mz_params_validate(&p, seq.len));
+        const uint64_t l = k_ + w_ - 1, nwin = seq.len >= l ? seq.len - l + 1 : 0;
+        uint64_t cap = (uint64_t)(nwin * 2.5 / (w_ + 1.0)) + 4096;
+        std::vector<uint32_t> pos, sk;
+        std::vector<uint64_t> val;
+        for (;;) {
+            pos.resize(cap);
+            if (sk_) sk.resize(cap);
+            if (p.value_bits) val.resize(cap);
+            mz_out out{pos.data(), sk_ ? sk.data() : nullptr, p.value_bits ? val.data() : nullptr, cap, 0};
+            int rc = mz_run(detail::thread_ctx(), &p, seq.data, seq.offset, seq.len, &out);
+            if (rc == MZ_ERR_CAPACITY) {
+                cap = out.count;
+                continue;
+            }
+            detail::check(rc);
+            pos.resize(out.count);
+            if (sk_) sk.resize(out.count);
+            if (p.value_bits) val.resize(out.count);
+            break;
+        }
+        // SIMD-collector quirk (src/collect.rs:257,267)
+        size_t skip = (!syncmer_ && !pos.empty() && !min_pos.empty() && pos[0] == min_pos.back()) ? 1 : 0;
+        min_pos.insert(min_pos.end(), pos.begin() + skip, pos.end());
+        if (sk_) sk_->insert(sk_->end(), sk.begin() + skip, sk.end());
+        if (skip && !val.empty()) val.erase(val.begin());
+        return Output(len, std::move(val), &min_pos);
+    }
+    std::vector<uint32_t> run_once(const PackedSeq& seq) const {
+        std::vector<uint32_t> v;
+        run(seq, v);
+        return v;
+    }
+
+private:
+    uint32_t k_, w_;
+    bool canonical_;
+    uint32_t syncmer_;
+    Hasher hasher_{};
+    bool has_hasher_ = false;
+    std::vector<uint32_t>* sk_ = nullptr;
+};
+
+inline Builder minimizers(uint32_t k, uint32_t w) { return {k, w, false, MZ_MODE_MINIMIZER}; }                     // src/lib.rs:240
+inline Builder canonical_minimizers(uint32_t k, uint32_t w) { return {k, w, true, MZ_MODE_MINIMIZER}; }            // :250
+inline Builder closed_syncmers(uint32_t k, uint32_t w) { return {k, w, false, MZ_MODE_CLOSED_SYNCMER}; }           // :269
+inline Builder canonical_closed_syncmers(uint32_t k, uint32_t w) { return {k, w, true, MZ_MODE_CLOSED_SYNCMER}; }  // :282
+inline Builder open_syncmers(uint32_t k, uint32_t w) { return {k, w, false, MZ_MODE_OPEN_SYNCMER}; }               // :301
+inline Builder canonical_open_syncmers(uint32_t k, uint32_t w) { return {k, w, true, MZ_MODE_OPEN_SYNCMER}; }      // :311
+inline Builder canonical_syncmers(uint32_t k, uint32_t w) { return canonical_closed_syncmers(k, w); }              // README.md:65
+inline std::vector<uint32_t> minimizer_positions(const PackedSeq& s, uint32_t k, uint32_t w) { return minimizers(k, w).run_once(s); }                      // :639
+inline std::vector<uint32_t> canonical_minimizer_positions(const PackedSeq& s, uint32_t k, uint32_t w) { return canonical_minimizers(k, w).run_once(s); }  // :652
+
+}  // namespace simd_minimizers

@@ -1,0 +1,177 @@
+//! Safe shim with the reference crate's builder surface (simd-minimizers v3.0.0,
+//! `src/lib.rs:225-654`): `minimizer_positions`, `canonical_minimizer_positions`,
+//! `minimizers/canonical_minimizers/closed_syncmers/.../canonical_open_syncmers(k, w)`,
+//! `.hasher(..)`, `.super_kmers(..)`, `.run(seq, &mut pos)`, `Output::values_u64()`.
+//! Bodies call the C ABI; nothing is computed on the CPU.  Not compiled in this repository's
+//! image (no Rust toolchain) -- see INTEGRATION.md.
+use mzb200_sys as sys;
+use seq_hash::packed_seq::{PackedSeq, Seq};
+use std::cell::RefCell;
+
+/// Hashers the device path understands: anything that is a per-base table with a fixed rotation.
+/// Sealed on purpose: an arbitrary `KmerHasher` cannot cross the ABI.
+pub trait TableHasher: sealed::Sealed {
+    fn k(&self) -> usize;
+    fn is_canonical(&self) -> bool;
+    /// Fill `f`, `c`, `rot`, `hash_canonical`.
+    fn fill(&self, p: &mut sys::mz_params);
+}
+mod sealed {
+    pub trait Sealed {}
+    impl<const RC: bool> Sealed for seq_hash::NtHasher<RC> {}
+    impl<const RC: bool> Sealed for seq_hash::MulHasher<RC> {}
+}
+impl<const RC: bool> TableHasher for seq_hash::NtHasher<RC> {
+    fn k(&self) -> usize { seq_hash::KmerHasher::k(self) }
+    fn is_canonical(&self) -> bool { RC }
+    fn fill(&self, p: &mut sys::mz_params) { unsafe { sys::mz_params_set_nthash(p, RC as u32); } }
+}
+impl<const RC: bool> TableHasher for seq_hash::MulHasher<RC> {
+    fn k(&self) -> usize { seq_hash::KmerHasher::k(self) }
+    fn is_canonical(&self) -> bool { RC }
+    fn fill(&self, p: &mut sys::mz_params) { unsafe { sys::mz_params_set_mulhash(p, RC as u32); } }
+}
+
+struct Ctx(*mut sys::mz_ctx);
+impl Drop for Ctx {
+    fn drop(&mut self) { unsafe { sys::mz_ctx_destroy(self.0) } }
+}
+thread_local! {
+    // the reference keeps its scratch thread_local too (src/lib.rs:217-219)
+    static CTX: RefCell<Option<Ctx>> = const { RefCell::new(None) };
+}
+fn with_ctx<R>(f: impl FnOnce(*mut sys::mz_ctx) -> R) -> R {
+    CTX.with_borrow_mut(|c| {
+        if c.is_none() {
+            let mut h = std::ptr::null_mut();
+            let rc = unsafe { sys::mz_ctx_create(std::ptr::null(), 0, &mut h) };
+            assert!(rc == sys::MZ_OK, "mzb200: {}", err(rc));
+            *c = Some(Ctx(h));
+        }
+        f(c.as_ref().unwrap().0)
+    })
+}
+fn err(rc: i32) -> String {
+    unsafe { std::ffi::CStr::from_ptr(sys::mz_strerror(rc)).to_string_lossy().into_owned() }
+}
+
+pub struct Builder<'h, const CANONICAL: bool, SkPos, const SYNCMER: u8> {
+    k: usize,
+    w: usize,
+    hasher: Option<&'h dyn TableHasher>,
+    sk_pos: SkPos,
+}
+pub struct Output<'o, const CANONICAL: bool> {
+    min_pos: &'o Vec<u32>,
+    vals: Vec<u64>,
+}
+impl<'o, const CANONICAL: bool> Output<'o, CANONICAL> {
+    pub fn values_u64(&self) -> impl ExactSizeIterator<Item = u64> + '_ { self.vals.iter().copied() }
+    pub fn pos_and_values_u64(&self) -> impl ExactSizeIterator<Item = (u32, u64)> + '_ {
+        self.min_pos.iter().copied().zip(self.vals.iter().copied())
+    }
+}
+
+macro_rules! ctor {
+    ($name:ident, $canon:literal, $sync:literal) => {
+        #[must_use]
+        pub const fn $name(k: usize, w: usize) -> Builder<'static, $canon, (), $sync> {
+            Builder { k, w, hasher: None, sk_pos: () }
+        }
+    };
+}
+ctor!(minimizers, false, 0);
+ctor!(canonical_minimizers, true, 0);
+ctor!(closed_syncmers, false, 1);
+ctor!(canonical_closed_syncmers, true, 1);
+ctor!(open_syncmers, false, 2);
+ctor!(canonical_open_syncmers, true, 2);
+/// README.md:65 name; alias of the closed variant.
+pub const fn canonical_syncmers(k: usize, w: usize) -> Builder<'static, true, (), 1> { canonical_closed_syncmers(k, w) }
+
+impl<'h, const CANONICAL: bool, const SYNCMER: u8> Builder<'h, CANONICAL, (), SYNCMER> {
+    #[must_use]
+    pub fn hasher<'h2>(&self, h: &'h2 dyn TableHasher) -> Builder<'h2, CANONICAL, (), SYNCMER> {
+        Builder { k: self.k, w: self.w, hasher: Some(h), sk_pos: () }
+    }
+    pub fn run<'o>(&self, seq: PackedSeq<'_>, min_pos: &'o mut Vec<u32>) -> Output<'o, CANONICAL> {
+        let vals = run_impl::<CANONICAL, SYNCMER>(self.k, self.w, self.hasher, seq, min_pos, None);
+        Output { min_pos, vals }
+    }
+    pub fn run_once(&self, seq: PackedSeq<'_>) -> Vec<u32> {
+        let mut v = vec![];
+        self.run(seq, &mut v);
+        v
+    }
+}
+impl<'h, const CANONICAL: bool> Builder<'h, CANONICAL, (), 0> {
+    #[must_use]
+    pub fn super_kmers<'o2>(&self, sk_pos: &'o2 mut Vec<u32>) -> Builder<'h, CANONICAL, &'o2 mut Vec<u32>, 0> {
+        Builder { k: self.k, w: self.w, hasher: self.hasher, sk_pos }
+    }
+}
+impl<'h, 'o2, const CANONICAL: bool> Builder<'h, CANONICAL, &'o2 mut Vec<u32>, 0> {
+    pub fn run<'o>(self, seq: PackedSeq<'_>, min_pos: &'o mut Vec<u32>) -> Output<'o, CANONICAL> {
+        let vals = run_impl::<CANONICAL, 0>(self.k, self.w, self.hasher, seq, min_pos, Some(self.sk_pos));
+        Output { min_pos, vals }
+    }
+}
+
+/// `Builder::run_impl` / `run_with_buf` (src/lib.rs:386-448, 554-576) -> one `mz_run` call.
+fn run_impl<const CANONICAL: bool, const SYNCMER: u8>(
+    k: usize, w: usize, hasher: Option<&dyn TableHasher>, seq: PackedSeq<'_>,
+    min_pos: &mut Vec<u32>, mut sk_pos: Option<&mut Vec<u32>>,
+) -> Vec<u64> {
+    let mut p = sys::mz_params::default();
+    unsafe { sys::mz_params_nthash(&mut p, k as u32, w as u32, SYNCMER as u32, CANONICAL as u32) };
+    if let Some(h) = hasher {
+        assert!(h.k() == k);
+        h.fill(&mut p);
+    }
+    let len = if SYNCMER != 0 { k + w - 1 } else { k };
+    p.want_sk = sk_pos.is_some() as u32;
+    p.value_bits = if len <= 32 { 64 } else { 0 };
+    let n = seq.len();
+    let rc = unsafe { sys::mz_params_validate(&p, n as u64) };
+    // the reference panics on these (assert!); keep its messages
+    assert!(rc == sys::MZ_OK, "{}", err(rc));
+    let nwin = (n + 1).saturating_sub(k + w - 1);
+    let mut cap = (nwin as f64 * 2.5 / (w as f64 + 1.0)) as usize + 4096;
+    let (bytes, offset) = seq.as_packed_bytes(); // (&[u8], bases into the first byte)
+    loop {
+        let start = min_pos.len();
+        min_pos.reserve(cap);
+        if let Some(sk) = sk_pos.as_deref_mut() { sk.reserve(cap); }
+        let mut vals: Vec<u64> = Vec::with_capacity(if p.value_bits != 0 { cap } else { 0 });
+        let mut out = sys::mz_out {
+            pos: min_pos.spare_capacity_mut().as_mut_ptr().cast(),
+            sk: sk_pos.as_deref_mut().map_or(std::ptr::null_mut(), |s| s.spare_capacity_mut().as_mut_ptr().cast()),
+            val: if p.value_bits != 0 { vals.as_mut_ptr() } else { std::ptr::null_mut() },
+            capacity: cap as u64,
+            count: 0,
+        };
+        let rc = with_ctx(|c| unsafe { sys::mz_run(c, &p, bytes.as_ptr(), offset as u64, n as u64, &mut out) });
+        if rc == sys::MZ_ERR_CAPACITY { cap = out.count as usize; continue; }
+        assert!(rc == sys::MZ_OK, "mzb200: {}", err(rc));
+        let m = out.count as usize;
+        // SIMD-collector quirk (src/collect.rs:257,267): drop the first new position if it repeats
+        // the caller's last one.
+        let skip = (SYNCMER == 0 && m > 0 && start > 0
+            && unsafe { *min_pos.as_ptr().add(start) } == min_pos[start - 1]) as usize;
+        unsafe {
+            if skip == 1 { std::ptr::copy(min_pos.as_ptr().add(start + 1), min_pos.as_mut_ptr().add(start), m - 1); }
+            min_pos.set_len(start + m - skip);
+            if let Some(sk) = sk_pos.as_deref_mut() {
+                let s0 = sk.len();
+                if skip == 1 { std::ptr::copy(sk.as_ptr().add(s0 + 1), sk.as_mut_ptr().add(s0), m - 1); }
+                sk.set_len(s0 + m - skip);
+            }
+            if p.value_bits != 0 { vals.set_len(m); }
+        }
+        if skip == 1 && !vals.is_empty() { vals.remove(0); }
+        return vals;
+    }
+}
+
+pub fn minimizer_positions(seq: PackedSeq<'_>, k: usize, w: usize) -> Vec<u32> { minimizers(k, w).run_once(seq) }
+pub fn canonical_minimizer_positions(seq: PackedSeq<'_>, k: usize, w: usize) -> Vec<u32> { canonical_minimizers(k, w).run_once(seq) }

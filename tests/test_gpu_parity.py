@@ -300,3 +300,18 @@ def test_batch_ragged_reads(sm, oracle):
         assert np.array_equal(offs, eo) and np.array_equal(pos, ep), (k, w, c, mode)
         if ev is not None:
             assert np.array_equal(vals, ev)
+
+
+def test_cpp_mirror_header(sm, tmp_path):
+    """include/simd_minimizers.hpp (the C++ host mirror) compiled with g++ against libmzb200.so
+    reproduces the reference's doc-test vectors."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    libdir = os.path.join(root, "simd-minimizers_b200")
+    exe = str(tmp_path / "cpp_mirror_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "cpp_mirror_test.cpp"), "-o", exe,
+                           "-L", libdir, "-lmzb200", "-Wl,-rpath," + libdir])
+    out = subprocess.check_output([exe]).decode()
+    assert "cpp mirror ok" in out
