@@ -30,10 +30,9 @@ class Params(C.Structure):
 
 def build(force: bool = False) -> str:
     """Compile the oracle with gcc (seconds)."""
-    src = os.path.join(_HERE, "mzoracle.c")
-    hdr = os.path.join(_HERE, "mzoracle.h")
+    srcs = [os.path.join(_HERE, f) for f in ("mzoracle.c", "mzoracle.h", "mzbaseline_avx2.c", "Makefile")]
     if (force or not os.path.exists(_LIB_PATH)
-            or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
+            or os.path.getmtime(_LIB_PATH) < max(os.path.getmtime(f) for f in srcs)):
         subprocess.check_call(["make", "-C", _HERE, "-B", "libmzoracle.so"],
                               stdout=subprocess.DEVNULL)
     return _LIB_PATH
@@ -74,6 +73,9 @@ def lib():
         L.mzo_values_u64.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint64, u64p]
         L.mzo_values_u128.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint64, u64p]
         L.mzo_synth_packed.argtypes = [C.c_uint64, C.c_uint64, u8p]
+        L.mzb_run_mt.argtypes = L.mzo_run_mt.argtypes
+        L.mzb_run_mt.restype = C.c_uint64
+        L.mzb_have_avx2.restype = C.c_int
         _lib = L
     return _lib
 
@@ -191,6 +193,27 @@ def run_mt(packed, off, n, params: Params, threads: int, want_sk=False, want_val
     if m == ERR:
         raise ValueError("oracle: run_mt failed (parameters or capacity)")
     return pos[:m], (sk[:m] if want_sk else None), (val[:m] if want_val else None)
+
+
+def baseline_run_mt(packed, off, n, params: Params, threads: int, want_sk=False, want_val=False,
+                    cap: int | None = None):
+    """8-lane AVX2 + pthreads CPU baseline (oracle/mzbaseline_avx2.c); scalar fallback inside."""
+    l = params.k + params.w - 1
+    nwin = max(0, n - l + 1)
+    if cap is None:
+        cap = max(nwin, 1)
+    pos = np.empty(cap, dtype=np.uint32)
+    sk = np.empty(cap, dtype=np.uint32) if want_sk else None
+    val = np.empty(cap, dtype=np.uint64) if want_val else None
+    m = lib().mzb_run_mt(_ptr(packed), off, n, C.byref(params), threads, _ptr(pos), _ptr(sk),
+                         _ptr(val), cap)
+    if m == ERR:
+        raise ValueError("baseline: run failed (parameters or capacity)")
+    return pos[:m], (sk[:m] if want_sk else None), (val[:m] if want_val else None)
+
+
+def have_avx2() -> bool:
+    return bool(lib().mzb_have_avx2())
 
 
 def values_u64(packed, off, length, canonical, pos: np.ndarray) -> np.ndarray:
