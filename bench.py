@@ -132,6 +132,18 @@ def measured_peak_gbs():
         return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic_bytes(config: str, n: int, world: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the
+    committed ncu capture of this exact command (profiles/traffic.json); None if not captured."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            t = json.load(f)
+        e = t.get(f"{config}:{n}:{world}")
+        return None if e is None else float(e["dram_bytes_read"] + e["dram_bytes_write"])
+    except Exception:
+        return None
+
+
 def oracle_params(o, cfg):
     hasher = o.make_hasher(cfg["hasher"], cfg["canonical"])
     return o.make_params(cfg["k"], cfg["w"], canonical=cfg["canonical"], mode=cfg["mode"], hasher=hasher)
@@ -344,11 +356,24 @@ def main():
                        "outputs": int(tot_count), "parallelism": f"{world} contiguous window shards, halo k+w-2 (+1 seam window)",
                        "l2": "input shard %.0f MB > 126 MB L2; outputs rewritten every step" % (n_local / 4e6)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": alg_bytes,
-                         "note": "integer-ALU bound kernel; see DESIGN.md for the op model"},
+                         "frac": achieved / peak, "traffic": ncu_traffic_bytes(args.config, n, world),
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": alg_bytes,
+                         "note": "kernel is integer-ALU bound, not HBM bound (ncu: ALU pipe ~72% "
+                                 "of peak, DRAM ~11%); alu_roofline gives the bound that applies"},
             "clocks": clocks, "gpu_launches": int(tot_launch),
         }
+        # north_star: "the roofline is the slower of bytes at HBM bandwidth and integer ops at
+        # ALU peak".  Op model of SURVEY 8(d): 35 int ops/bp canonical pos+values, 17 forward,
+        # 39 syncmers+u128; ALU-pipe peak = SMs x 64 lanes/clk (LOP3/SHF/IMNMX/PRMT share one
+        # pipe, B300_MICROARCH 'rt_SMSP=2') x the SM clock sampled during the timed region.
+        ops_bp = {"c1": 17.0, "c2": 35.0, "c3": 35.0, "c4": 39.0}[args.config]
+        sm_clock = (clocks.get("sm_mhz") or 1965.0) * 1e6
+        alu_peak = 148 * 64 * sm_clock
+        gbp_rank = (n_local / (float(np.mean(dev_ms)) * 1e-3))
+        line["alu_roofline"] = {"model_int_ops_per_bp": ops_bp, "peak_int_ops_per_s": alu_peak,
+                                "achieved_int_ops_per_s": gbp_rank * ops_bp,
+                                "frac": gbp_rank * ops_bp / alu_peak,
+                                "source": "SURVEY.md 8(d) op model; 148 SMs x 64 ALU lanes/clk x sampled SM clock"}
         if not args.no_e2e:
             line["e2e"] = {"value": n / (e2e_ms_max * 1e-3) / 1e9, "unit": "Gbp/s",
                            "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": int(h2d_bytes),

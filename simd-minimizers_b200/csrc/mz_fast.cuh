@@ -408,8 +408,8 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     // the very first thread of the sequence)
                     const uint32_t hp = (minim && !(j00 == 0 && t2 == 0)) ? 1u : 0u;
                     const uint32_t rel = t2 * a.S - hp + hp0 + local;  // bases from the tile's bit0
-                    opos[x] = pos00 - hp0 + rel;
-                    if (a.want_sk) a.sk[gbase + cbase + x] = pos00 + t2 * a.S + (jl - hp);
+                    __stcs(opos + x, pos00 - hp0 + rel);  // streaming store: keep the L2 for the scratch rows
+                    if (a.want_sk) __stcs(a.sk + (gbase + cbase + x), pos00 + t2 * a.S + (jl - hp));
                     if (a.value_bits == 64) {
                         const uint32_t pbit = tsh + 2u * rel, wl = pbit >> 5, sh = pbit & 31u;
                         uint32_t w0, w1, w2;
@@ -428,7 +428,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                             const uint64_t r = (swap_pairs64(__brevll(v)) ^ 0xAAAAAAAAAAAAAAAAull) >> (64 - 2 * len);
                             v = r < v ? r : v;
                         }
-                        a.val[gbase + cbase + x] = v;
+                        __stcs(reinterpret_cast<unsigned long long*>(a.val) + (gbase + cbase + x), (unsigned long long)v);
                     } else if (a.value_bits == 128) {
                         uint64_t lo, hi;
                         kmer_value_u128(a, tbit0 + 2ull * rel, a.val_len, canon_val, lo, hi);
