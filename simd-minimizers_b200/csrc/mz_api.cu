@@ -186,6 +186,7 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
         if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS * 2))) return rc;
         a.scratch = d.rows.p;
         a.scratch_words_per_block = fp.scratch_words_per_block;
+        a.list_cap = fp.list_cap;
     } else {
         rc = plan_generic(d, p, wend - wbeg, &pl);
     }
@@ -723,7 +724,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     Plan pl;
     mz::FastPlan fp;
     bool fast = p->w <= mz::FAST_MAX_W && !(p->hash_canonical && !p->strand_tiebreak) &&
-                mz::fast_smem(S, p->w) <= 56 * 1024 && (uint64_t)S + p->w + 2 < 65535;
+                mz::fast_smem(S, p->w, mz::fast_list_cap(S, *p)) <= 56 * 1024 && (uint64_t)S + p->w + 2 < 65535;
     if (fast) {
         const uint64_t tiles = (n_reads + 31) / 32;
         if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
@@ -731,6 +732,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         fp.num_tiles = (uint32_t)tiles;
         fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * 4);
         fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
+        fp.list_cap = mz::fast_list_cap(S, *p);
         pl.num_tiles = fp.num_tiles;
     } else {
         const bool lr = p->strand_tiebreak != 0;
@@ -792,6 +794,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS * 2))) return rc;
             a.scratch = d.rows.p;
             a.scratch_words_per_block = fp.scratch_words_per_block;
+            a.list_cap = fp.list_cap;
             rc = mz::launch_fast(*p, fp.grid, a, d.stream);
         } else {
             rc = launch_generic(*p, pl, a, d.stream);

@@ -37,6 +37,7 @@ struct KArgs {
     uint32_t num_tiles;
     uint32_t* scratch;                 // fast kernel: per-block record rows (L2-resident)
     uint64_t scratch_words_per_block;
+    uint32_t list_cap;                 // fast kernel: staging entries per warp and pass
     // batch mode (thread per read); reads == 0 -> single sequence
     uint64_t n_reads;
     const uint64_t* read_start_bp;   // may be null -> fixed stride

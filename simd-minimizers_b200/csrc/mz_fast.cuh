@@ -40,10 +40,16 @@ inline size_t fast_scratch_words(uint32_t S, uint32_t W) {
     return (size_t)fast_nb(S, W) * fast_wq(W) * 32;
 }
 constexpr uint32_t FAST_WARPS = FAST_NT / 32;
-constexpr uint32_t FAST_LIST = 1024;  // staging entries per warp and pass
 // shared memory: table | misc | per-warp staging list | per-warp flag words (2 tiles in flight)
-inline size_t fast_smem(uint32_t S, uint32_t W) {
-    return 256 * 16 + 32 + FAST_WARPS * FAST_LIST * 4 + (size_t)FAST_WARPS * 2 * fast_nb(S, W) * 32 * 4;
+inline size_t fast_smem(uint32_t S, uint32_t W, uint32_t list_cap) {
+    return 256 * 16 + 32 + (size_t)FAST_WARPS * list_cap * 4 + (size_t)FAST_WARPS * 2 * fast_nb(S, W) * 32 * 4;
+}
+// staging entries per warp: 1.5x the expected emissions of a tile (a second pass handles more)
+inline uint32_t fast_list_cap(uint32_t S, const mz_params& p) {
+    const double dens = p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
+                      : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
+    const uint32_t want = (uint32_t)(32.0 * S * dens * 1.5) + 64;
+    return std::min<uint32_t>(std::max<uint32_t>((want + 127) / 128 * 128, 256), 4096);
 }
 
 // Rare path (leftmost != rightmost minimum): strand rule 2*#TG > l on the window's l bases
@@ -78,6 +84,12 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 __device__ __forceinline__ void or_if_ne(uint32_t& bf, uint32_t a, uint32_t b, uint32_t bit) {
     asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bf) : "r"(a), "r"(b), "r"(bit));
 }
+// a*b + c issued as IMAD (FMA pipe) -- `b` is an opaque 1 so ptxas cannot turn it into an ALU add
+__device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
 // J is a compile-time constant after unrolling
 __device__ __forceinline__ uint32_t put_byte(uint32_t acc, uint32_t v, int J) {  // acc.byte[J] = v.byte[0]
     return __byte_perm(acc, v, J == 0 ? 0x3214 : J == 1 ? 0x3240 : J == 2 ? 0x3410 : 0x4210);
@@ -95,10 +107,11 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint4* T = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* misc = reinterpret_cast<uint32_t*>(T + 256);
-    uint32_t* const list = misc + 8 + warp * FAST_LIST;  // this warp's staging list
+    const uint32_t LCAP = a.list_cap;
+    uint32_t* const list = misc + 8 + warp * LCAP;  // this warp's staging list
     const uint32_t NBmax = fast_nb(a.S, W);
     // flag words of this warp, two tiles in flight: fl0[buf][b*32 + lane]
-    uint32_t* const fl0 = misc + 8 + FAST_WARPS * FAST_LIST + (size_t)warp * 2 * NBmax * 32;
+    uint32_t* const fl0 = misc + 8 + FAST_WARPS * LCAP + (size_t)warp * 2 * NBmax * 32;
     // this warp's record rows in global scratch (two buffers): row r, lane t -> sc0[buf][r*32 + t]
     uint32_t* const sc0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * 2 * a.scratch_words_per_block;
 
@@ -122,6 +135,8 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
         misc[2] = ca;
     }
     const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T);
+    uint32_t one;
+    asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque constant 1 for imad()
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
     const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (W - 1) / 2, so2 = a.mode == MODE_CLOSED ? W - 1 : (W - 1) / 2;
 
@@ -218,62 +233,96 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                 uint32_t accL[WQ], accR[WQ];
 #pragma unroll
                 for (int q = 0; q < WQ; q++) accL[q] = 0, accR[q] = 0;
-                uint32_t hpair = 0;
+                // Two k-mers per step: one table load gives both hashes; the prefix minimum and
+                // the first window of the pair use the 3-input VIMNMX3.
 #pragma unroll
-                for (int t = 0; t < W; t++) {
-                    uint32_t h;
-                    if ((t & 1) == 0) {
-                        const uint32_t word = N[(t >> 4) * 2 + ((t >> 1) & 1)];
-                        const uint32_t idx = get_byte(word, (t & 15) >> 2);
-                        const uint32_t addr = idx * 16u + tb;
-                        if (HC) {
-                            const uint4 e = lds128(addr);
-                            const uint32_t fA = rotl32(fw, R) ^ e.x, rA = rotr32(rc, R) ^ e.z;
-                            h = fA + rA;
-                            if (t + 1 < W) {
-                                fw = rotl32(fw, R2) ^ e.y;
-                                rc = rotr32(rc, R2) ^ e.w;
-                                hpair = fw + rc;
-                            } else {
-                                fw = fA;
-                                rc = rA;
-                            }
+                for (int t = 0; t < W; t += 2) {
+                    const bool two = t + 1 < W;
+                    const uint32_t word = N[(t >> 4) * 2 + ((t >> 1) & 1)];
+                    const uint32_t idx = get_byte(word, (t & 15) >> 2);
+                    const uint32_t addr = idx * 16u + tb;
+                    uint32_t h0, h1 = 0;
+                    if (HC) {
+                        const uint4 e = lds128(addr);
+                        const uint32_t fA = rotl32(fw, R) ^ e.x, rA = rotr32(rc, R) ^ e.z;
+                        h0 = fA + rA;
+                        if (two) {
+                            fw = rotl32(fw, R2) ^ e.y;
+                            rc = rotr32(rc, R2) ^ e.w;
+                            h1 = fw + rc;
                         } else {
-                            const uint2 e = lds64(addr);
-                            const uint32_t fA = rotl32(fw, R) ^ e.x;
-                            h = fA;
-                            if (t + 1 < W) {
-                                fw = rotl32(fw, R2) ^ e.y;
-                                hpair = fw;
-                            } else {
-                                fw = fA;
-                            }
+                            fw = fA;
+                            rc = rA;
                         }
                     } else {
-                        h = hpair;
+                        const uint2 e = lds64(addr);
+                        const uint32_t fA = rotl32(fw, R) ^ e.x;
+                        h0 = fA;
+                        if (two) {
+                            fw = rotl32(fw, R2) ^ e.y;
+                            h1 = fw;
+                        } else {
+                            fw = fA;
+                        }
                     }
-                    const uint32_t pos = eb + t;
-                    const uint32_t le = (h & 0xffff0000u) | pos;
-                    preL = t == 0 ? le : min(preL, le);
-                    const uint32_t res = t < W - 1 ? min(preL, RL[t < W - 1 ? t + 1 : 0]) : preL;
-                    RL[t] = le;
+                    // positions: eb + t on the FMA pipe (IMAD with an opaque 1), the ALU pipe is the bottleneck
+                    const uint32_t pos0 = imad(eb, one, t), pos1 = imad(eb, one, t + 1);
+                    const uint32_t le0 = (h0 & 0xffff0000u) | pos0, le1 = (h1 & 0xffff0000u) | pos1;
+                    uint32_t res0, res1 = 0, mR0 = 0, mR1 = 0;
+                    {
+                        const uint32_t s1 = t + 1 < W ? RL[t + 1 < W ? t + 1 : 0] : 0u;
+                        const uint32_t s2 = t + 2 < W ? RL[t + 2 < W ? t + 2 : 0] : 0u;
+                        if (t == 0) {
+                            res0 = W > 1 ? min(le0, s1) : le0;
+                            preL = two ? min(le0, le1) : le0;
+                        } else {
+                            res0 = t + 1 < W ? __vimin3_u32(preL, le0, s1) : min(preL, le0);
+                            preL = two ? __vimin3_u32(preL, le0, le1) : min(preL, le0);
+                        }
+                        if (two) res1 = t + 2 < W ? min(preL, s2) : preL;
+                        RL[t] = le0;
+                        if (two) RL[t + 1] = le1;
+                    }
                     if (LR) {
-                        const uint32_t re = le ^ 0xffff0000u;
-                        preR = t == 0 ? re : max(preR, re);
-                        const uint32_t mR = t < W - 1 ? max(preR, RR[t < W - 1 ? t + 1 : 0]) : preR;
-                        RR[t] = re;
-                        tacc |= res ^ mR;  // low half != 0  <=>  leftmost != rightmost
-                        accR[t >> 2] = put_byte(accR[t >> 2], mR, t & 3);
-                        if (t == W - 1) lastR = mR;
+                        const uint32_t re0 = le0 ^ 0xffff0000u, re1 = le1 ^ 0xffff0000u;
+                        const uint32_t s1 = t + 1 < W ? RR[t + 1 < W ? t + 1 : 0] : 0u;
+                        const uint32_t s2 = t + 2 < W ? RR[t + 2 < W ? t + 2 : 0] : 0u;
+                        if (t == 0) {
+                            mR0 = W > 1 ? max(re0, s1) : re0;
+                            preR = two ? max(re0, re1) : re0;
+                        } else {
+                            mR0 = t + 1 < W ? __vimax3_u32(preR, re0, s1) : max(preR, re0);
+                            preR = two ? __vimax3_u32(preR, re0, re1) : max(preR, re0);
+                        }
+                        if (two) mR1 = t + 2 < W ? max(preR, s2) : preR;
+                        RR[t] = re0;
+                        if (two) RR[t + 1] = re1;
+                        tacc |= res0 ^ mR0;  // low half != 0  <=>  leftmost != rightmost
+                        accR[t >> 2] = put_byte(accR[t >> 2], mR0, t & 3);
+                        if (two) {
+                            tacc |= res1 ^ mR1;
+                            accR[(t + 1) >> 2] = put_byte(accR[(t + 1) >> 2], mR1, (t + 1) & 3);
+                        }
+                        if (t == W - 1) lastR = mR0;
+                        if (t + 1 == W - 1) lastR = mR1;
                     }
                     if (SYNC) {
-                        const uint32_t d = pos - (res & 0xffffu);
-                        if (d == so1 || d == so2) bf |= 1u << t;
+                        const uint32_t d0 = pos0 - (res0 & 0xffffu);
+                        if (d0 == so1 || d0 == so2) bf |= 1u << t;
+                        if (two) {
+                            const uint32_t d1 = pos1 - (res1 & 0xffffu);
+                            if (d1 == so1 || d1 == so2) bf |= 1u << (t + 1);
+                        }
                     } else {
-                        or_if_ne(bf, res, prev, 1u << t);
-                        prev = res;
+                        or_if_ne(bf, res0, prev, 1u << t);
+                        prev = res0;
+                        if (two) {
+                            or_if_ne(bf, res1, prev, 1u << (t + 1));
+                            prev = res1;
+                        }
                     }
-                    accL[t >> 2] = put_byte(accL[t >> 2], res, t & 3);
+                    accL[t >> 2] = put_byte(accL[t >> 2], res0, t & 3);
+                    if (two) accL[(t + 1) >> 2] = put_byte(accL[(t + 1) >> 2], res1, (t + 1) & 3);
                 }
                 // suffix minima of this block (slot 0 is never needed)
 #pragma unroll
@@ -368,11 +417,11 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
         const uint32_t pos00 = (uint32_t)j00;
 
         // Every lane walks its own flag words (coalesced across lanes) and stages its entries at
-        // [toff, toff + cnt) of the tile's output range; FAST_LIST entries per pass.
+        // [toff, toff + cnt) of the tile's output range; list_cap entries per pass.
         uint32_t bq = 0, produced = 0;
         uint32_t f = (cnt_e != 0) ? flr[0] : 0u;
-        for (uint32_t cbase = 0; cbase < total; cbase += FAST_LIST) {
-            while (produced < cnt_e && toff + produced < cbase + FAST_LIST) {
+        for (uint32_t cbase = 0; cbase < total; cbase += LCAP) {
+            while (produced < cnt_e && toff + produced < cbase + LCAP) {
                 while (f == 0) {
                     bq++;
                     f = flr[bq * 32];
@@ -383,7 +432,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                 produced++;
             }
             __syncwarp();
-            const uint32_t nent = min(FAST_LIST, total - cbase);
+            const uint32_t nent = min(LCAP, total - cbase);
             uint32_t* const opos = a.pos + (gbase + cbase);
             // sweep 1: fetch each entry's position byte from the L2 scratch (independent loads,
             // unrolled so several are in flight) and fold it into the staged descriptor
@@ -460,7 +509,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
 
 // ---- host side ---------------------------------------------------------------------------
 struct FastPlan {
-    uint32_t S = 0, num_tiles = 0, grid = 0;
+    uint32_t S = 0, num_tiles = 0, grid = 0, list_cap = 0;
     size_t scratch_words_per_block = 0;
 };
 
@@ -478,16 +527,17 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     } else {
         // long segments amortise the (k+w-2)-base warm-up; keep >= ~3 tiles per resident block
         uint64_t want = nwin / (slots * 3 * 32);
-        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 256);
+        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 288);
     }
     s = std::max<uint32_t>(16, (s + 15) / 16 * 16);
     // flag words live in shared memory (one per W windows): keep ~4 blocks per SM resident
-    while (s > 16 && fast_smem(s, p.w) > 56 * 1024) s -= 16;
+    while (s > 16 && fast_smem(s, p.w, fast_list_cap(s, p)) > 56 * 1024) s -= 16;
     if ((uint64_t)s + p.w + 2 >= 65535) return false;
     const uint64_t Tt = (uint64_t)32 * s;
     const uint64_t tiles = (nwin + Tt - 1) / Tt;
     if (tiles == 0 || tiles > 0x7fffffffull) return false;
     pl->S = s;
+    pl->list_cap = fast_list_cap(s, p);
     pl->num_tiles = (uint32_t)tiles;
     pl->grid = (uint32_t)std::min<uint64_t>((tiles + FAST_WARPS - 1) / FAST_WARPS, (uint64_t)sm_count * bps);
     pl->scratch_words_per_block = fast_scratch_words(s, p.w);
@@ -497,7 +547,7 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
 template <int W, bool HC, bool LR, bool SYNC>
 inline int launch_fast_inst(uint32_t grid, const KArgs& a, cudaStream_t st) {
     auto kern = mz_fast_kernel<W, HC, LR, SYNC>;
-    const size_t smem = fast_smem(a.S, W);
+    const size_t smem = fast_smem(a.S, W, a.list_cap);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return MZ_ERR_CUDA;
