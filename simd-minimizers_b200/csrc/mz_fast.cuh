@@ -159,16 +159,6 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
 
         if (sg.nvalid) {
             uint32_t fw = misc[1], rc = misc[2];
-            // ---- prologue: k-1 bases, one at a time (leaving base = virtual 'A') -------------
-            {
-                BaseReader in;
-                in.init(a, sg.bit0);
-                for (uint32_t u = 0; u + 1 < k; u++) {
-                    const uint4 e = T[in.next(a)];
-                    fw = rotl32(fw, R) ^ e.x;
-                    if (HC) rc = rotr32(rc, R) ^ e.z;
-                }
-            }
             const uint32_t nelem = sg.nvalid + sg.has_prev + (W - 1);
             NB = (nelem + W - 1) / W;
             // first/last valid window-end element: e = jl + W - 1, jl in [has_prev, has_prev + nvalid)
@@ -183,6 +173,27 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             const uint32_t sh0 = (uint32_t)sg.bit0 & 31u;
             const uint64_t remw = a.seq_nwords - 1 - w0abs;
             const uint32_t wlim = remw > 0x7ffffff0ull ? 0x7ffffff0u : (uint32_t)remw;
+            // ---- prologue: consume k-1 bases, two per table step (leaving bases = virtual 'A') --
+            {
+                uint32_t pp = sh0, rem = k - 1;
+                while (rem) {
+                    const uint32_t wl = pp >> 5, sh = pp & 31u;
+                    uint32_t x = __funnelshift_r(__ldg(wbase + min(wl, wlim)), __ldg(wbase + min(wl + 1, wlim)), sh);
+                    uint32_t take = min(rem, 16u);
+                    rem -= take;
+                    pp += 32u;
+                    for (; take >= 2; take -= 2, x >>= 4) {
+                        const uint4 e = T[x & 15u];
+                        fw = rotl32(fw, R2) ^ e.y;
+                        if (HC) rc = rotr32(rc, R2) ^ e.w;
+                    }
+                    if (take) {
+                        const uint4 e = T[x & 3u];
+                        fw = rotl32(fw, R) ^ e.x;
+                        if (HC) rc = rotr32(rc, R) ^ e.z;
+                    }
+                }
+            }
             uint32_t pin = sh0 + 32u + 2u * (k - 1);  // bit position (+32) of the entering stream
             uint32_t pout = sh0 + 30u;                // bit position (+32) of the leaving stream
             // may any (pre)fetch of this thread touch a word past the end of the buffer?
@@ -357,7 +368,8 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                 }
                 prevlow = get_byte(accL[(W - 1) >> 2], (W - 1) & 3);
                 // keep flags of valid windows only: bit t <-> window-end element eb + t
-                {
+                // (only the first and last blocks of a segment can hold invalid windows)
+                if (eb < e_lo + 1u || eb + W > e_hi) {
                     const uint32_t lo = e_lo > eb ? min(e_lo - eb, (uint32_t)W) : 0u;
                     const uint32_t hi = e_hi > eb ? min(e_hi - eb, (uint32_t)W) : 0u;
                     const uint32_t mhi = hi >= 32u ? 0xffffffffu : ((1u << hi) - 1u);
