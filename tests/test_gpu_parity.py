@@ -315,3 +315,66 @@ def test_cpp_mirror_header(sm, tmp_path):
                            "-L", libdir, "-lmzb200", "-Wl,-rpath," + libdir])
     out = subprocess.check_output([exe]).decode()
     assert "cpp mirror ok" in out
+
+
+def test_full_size_genome_properties(sm, oracle):
+    """BASELINE config 2/3 at full size (3.1 Gbp, canonical k=31 w=19, pos + super-k-mer starts +
+    u64 values): size-independent properties, exact oracle compare on the first / last million
+    windows and random tiles, and checksum agreement between the chunk-pipelined host path and a
+    single device-resident launch (two different seam decompositions of the same sequence)."""
+    import ctypes as C
+    import importlib
+
+    import torch
+
+    import bench
+
+    n, k, w = 3_100_000_000, 31, 19
+    l = k + w - 1
+    nwin = n - l + 1
+    packed, off = bench.synth_packed_range(bench.SEED, 0, n)
+    packed = np.ascontiguousarray(packed)
+    seq = sm.PackedSeq(packed, off, n)
+    pos, sk = sm.U32Vec(), sm.U32Vec()
+    out = sm.canonical_minimizers(k, w).super_kmers(sk).run(seq, pos)
+    vals = out.values_u64()
+    p, s = pos.array, sk.array
+    m = len(p)
+    assert len(s) == m and len(vals) == m
+    assert abs(m / n - 2.0 / (w + 1)) < 0.002                      # density of random minimizers
+    assert int(p.max()) <= n - k and s[0] == 0 and int(s[-1]) < nwin
+    assert (np.diff(s.astype(np.int64)) > 0).all()                 # one emission per window at most, in order
+    assert (p[1:] != p[:-1]).all()                                 # adjacent duplicates removed
+    d = p.astype(np.int64) - s.astype(np.int64)
+    assert d.min() >= 0 and d.max() <= w - 1                       # minimizer lies inside its first window
+    pr = oracle.make_params(k, w, canonical=True)
+    rng = np.random.default_rng(1)
+    ranges = [(0, 1_000_000), (nwin - 1_000_000, nwin)] + [
+        (a, a + 200_000) for a in (int(x) for x in rng.integers(1_000_000, nwin - 2_000_000, 3))]
+    for a, b in ranges:
+        epos, esk = oracle.run_range(packed, off, n, pr, a, b, want_sk=True)
+        i0, i1 = np.searchsorted(s, a, "left"), np.searchsorted(s, b, "left")
+        assert np.array_equal(p[i0:i1], epos) and np.array_equal(s[i0:i1], esk), (a, b)
+        assert np.array_equal(vals[i0:i1], oracle.values_u64(packed, off, k, True, epos)), (a, b)
+    # same sequence, one device-resident launch: identical streams (checksums + exact on device)
+    ffi = importlib.import_module("simd-minimizers_b200._ffi")
+    L = ffi.lib()
+    d_in = torch.from_numpy(packed).cuda()
+    dp = torch.empty(m, dtype=torch.int32, device="cuda")
+    ds = torch.empty(m, dtype=torch.int32, device="cuda")
+    dv = torch.empty(m, dtype=torch.int64, device="cuda")
+    prm = ffi.MzParams()
+    L.mz_params_nthash(C.byref(prm), k, w, 0, 1)
+    prm.want_sk, prm.value_bits = 1, 64
+    o2 = ffi.MzOut(dp.data_ptr(), ds.data_ptr(), dv.data_ptr(), m, 0)
+    ctx = sm.Context()
+    assert L.mz_run_device(ctx.handle, 0, C.byref(prm), d_in.data_ptr(), off, n, 0, 0, C.byref(o2)) == 0
+    assert o2.count == m
+    hp = torch.from_numpy(p.view(np.int32)).cuda()
+    assert torch.equal(hp, dp)
+    del hp
+    hs = torch.from_numpy(s.view(np.int32)).cuda()
+    assert torch.equal(hs, ds)
+    del hs
+    hv = torch.from_numpy(vals.view(np.int64)).cuda()
+    assert torch.equal(hv, dv)
