@@ -155,6 +155,17 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
                  uint64_t n_reads, const uint64_t* read_start_bp, const uint32_t* read_len_bp,
                  uint64_t stride_bytes, uint32_t fixed_len_bp, uint64_t* out_offsets, mz_out* out);
 
+/*
+ * ASCII ingestion on the device (the step before the path).  `AsciiSeq` /
+ * `PackedSeqVec::from_ascii` map a character to its 2-bit code with (c >> 1) & 3
+ * (A/a=0 C/c=1 T/t=2 G/g=3; callers bench/src/lib.rs:48-82 pack on the host first).
+ * mz_pack_ascii packs n characters into (n+3)/4 bytes of PackedSeq storage (host in, host out);
+ * mz_run_ascii packs on the device and runs the path without the packed bytes ever visiting
+ * the host.  Results equal mz_run on the packed sequence.
+ */
+int mz_pack_ascii(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out);
+int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out);
+
 int mz_last_timing(const mz_ctx* ctx, mz_timing* t);
 
 #ifdef __cplusplus

@@ -89,5 +89,8 @@ extern "C" {
                         packed_bytes: u64, n_reads: u64, read_start_bp: *const u64,
                         read_len_bp: *const u32, stride_bytes: u64, fixed_len_bp: u32,
                         out_offsets: *mut u64, out: *mut mz_out) -> c_int;
+    pub fn mz_pack_ascii(ctx: *mut mz_ctx, ascii: *const c_char, n: u64, packed_out: *mut u8) -> c_int;
+    pub fn mz_run_ascii(ctx: *mut mz_ctx, p: *const mz_params, ascii: *const c_char, n: u64,
+                        out: *mut mz_out) -> c_int;
     pub fn mz_last_timing(ctx: *const mz_ctx, t: *mut mz_timing) -> c_int;
 }

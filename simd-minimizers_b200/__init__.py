@@ -27,7 +27,7 @@ from . import _ffi
 from ._ffi import MzError, MzOut, MzParams, MzTiming
 
 __all__ = [
-    "PackedSeq", "PackedSeqVec", "NtHasher", "MulHasher", "U32Vec", "Builder", "Output",
+    "PackedSeq", "PackedSeqVec", "AsciiSeq", "NtHasher", "MulHasher", "U32Vec", "Builder", "Output",
     "minimizers", "canonical_minimizers", "closed_syncmers", "canonical_closed_syncmers",
     "open_syncmers", "canonical_open_syncmers", "canonical_syncmers", "minimizer_positions",
     "canonical_minimizer_positions", "Context", "default_context", "MzError",
@@ -114,6 +114,32 @@ class PackedSeqVec:
 
     def slice(self, start: int, end: int) -> PackedSeq:
         return self.as_slice().slice(start, end)
+
+
+class AsciiSeq:
+    """ASCII DNA text (packed_seq::AsciiSeq): characters map to 2-bit codes with (c >> 1) & 3,
+    so ACTGactg work and anything else aliases silently, as in the reference.  Packed on the
+    device (mz_run_ascii); never packed on the host."""
+
+    def __init__(self, seq: bytes):
+        self.seq = bytes(seq)
+        self.len = len(self.seq)
+
+    def __len__(self):
+        return self.len
+
+    def as_slice(self) -> "AsciiSeq":
+        return self
+
+    def slice(self, start: int, end: int) -> "AsciiSeq":
+        return AsciiSeq(self.seq[start:end])
+
+    def pack(self, ctx: "Context | None" = None) -> "PackedSeqVec":
+        """PackedSeqVec::from_ascii, computed on the device (mz_pack_ascii)."""
+        data = np.zeros((self.len + 3) // 4 + _PAD, dtype=np.uint8)
+        ctx = ctx or default_context()
+        _check(_ffi.lib().mz_pack_ascii(ctx.handle, self.seq, self.len, data.ctypes.data))
+        return PackedSeqVec(data, self.len)
 
 
 # ------------------------------------------------------------------------------------------
@@ -336,7 +362,10 @@ class Builder:
             val = np.empty(max(cap, 1) * max(vw, 1), dtype=np.uint64) if vw else None
             out = MzOut(pos.ctypes.data, sk.ctypes.data if sk is not None else None,
                         val.ctypes.data if val is not None else None, cap, 0)
-            rc = L.mz_run(ctx.handle, C.byref(p), seq.data.ctypes.data, seq.offset, n, C.byref(out))
+            if isinstance(seq, AsciiSeq):
+                rc = L.mz_run_ascii(ctx.handle, C.byref(p), seq.seq, n, C.byref(out))
+            else:
+                rc = L.mz_run(ctx.handle, C.byref(p), seq.data.ctypes.data, seq.offset, n, C.byref(out))
             if rc == _ffi.MZ_ERR_CAPACITY:
                 cap = int(out.count)
                 continue

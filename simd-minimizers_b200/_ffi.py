@@ -27,7 +27,7 @@ SYMBOLS = [
     "mz_abi_version", "mz_strerror", "mz_last_error", "mz_device_count", "mz_params_nthash",
     "mz_params_mulhash", "mz_params_set_nthash", "mz_params_set_mulhash", "mz_params_validate",
     "mz_ctx_create", "mz_ctx_destroy", "mz_ctx_device_count", "mz_host_alloc", "mz_host_free",
-    "mz_run", "mz_run_device", "mz_run_batch", "mz_last_timing",
+    "mz_run", "mz_run_device", "mz_run_batch", "mz_pack_ascii", "mz_run_ascii", "mz_last_timing",
 ]
 
 
@@ -90,6 +90,8 @@ def lib():
                                 C.c_uint64, C.c_uint64, C.POINTER(MzOut)]
     L.mz_run_batch.argtypes = [vp, C.POINTER(MzParams), vp, C.c_uint64, C.c_uint64, vp, vp,
                                C.c_uint64, C.c_uint32, vp, C.POINTER(MzOut)]
+    L.mz_pack_ascii.argtypes = [vp, C.c_char_p, C.c_uint64, vp]
+    L.mz_run_ascii.argtypes = [vp, C.POINTER(MzParams), C.c_char_p, C.c_uint64, C.POINTER(MzOut)]
     L.mz_last_timing.argtypes = [vp, C.POINTER(MzTiming)]
     _lib = L
     return L

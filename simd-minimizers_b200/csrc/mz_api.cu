@@ -74,6 +74,7 @@ struct DevState {
     DevBuf<unsigned long long> scratch;  // [0]=count [1]=ticket|overflow [2..]=tile_state
     DevBuf<uint32_t> rows;               // fast kernel per-block record rows
     DevBuf<uint8_t> in;
+    DevBuf<uint8_t> ascii;               // mz_pack_ascii / mz_run_ascii staging
     DevBuf<uint32_t> pos, sk;
     DevBuf<uint64_t> val;
     DevBuf<uint64_t> offs;  // batch CSR offsets
@@ -347,6 +348,46 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
     return too_small ? MZ_ERR_CAPACITY : MZ_OK;
 }
 
+// ASCII -> 2-bit packing, (c >> 1) & 3 per character; one thread per 16 characters.
+__global__ void mz_pack_ascii_kernel(const uint8_t* __restrict__ ascii, uint64_t n,
+                                     uint32_t* __restrict__ out, uint64_t nwords) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const uint64_t base = i * 16;
+    uint32_t w = 0;
+    if (base + 16 <= n) {
+        const uint4 v = *reinterpret_cast<const uint4*>(ascii + base);
+        const uint32_t q[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t codes = (q[j] >> 1) & 0x03030303u;
+            // gather the four 2-bit codes into one byte (multiply-shift, no carries collide)
+            w |= ((codes * 0x01041040u) >> 24) << (8 * j);
+        }
+    } else {
+        for (uint64_t j = 0; base + j < n; j++) w |= (uint32_t)((ascii[base + j] >> 1) & 3u) << (2 * j);
+    }
+    out[i] = w;
+}
+
+// ascii (host) -> d.ascii -> packed words in d.in; returns packed byte count
+int pack_on_device(DevState& d, const char* ascii, uint64_t n, size_t* nbytes_out, uint32_t* launches) {
+    const uint64_t nwords = (n + 15) / 16;
+    int rc;
+    if ((rc = d.ascii.reserve(n + 16))) return rc;
+    if ((rc = d.in.reserve(nwords * 4 + 64))) return rc;
+    CK(cudaMemcpyAsync(d.ascii.p, ascii, n, cudaMemcpyHostToDevice, d.stream));
+    if (nwords) {
+        const uint32_t nt = 256;
+        mz_pack_ascii_kernel<<<(unsigned)((nwords + nt - 1) / nt), nt, 0, d.stream>>>(
+            d.ascii.p, n, reinterpret_cast<uint32_t*>(d.in.p), nwords);
+        CK(cudaGetLastError());
+        if (launches) (*launches)++;
+    }
+    *nbytes_out = (size_t)nwords * 4;
+    return MZ_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -482,7 +523,7 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         DevState& d = *dp;
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
-        d.scratch.release(), d.rows.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
+        d.scratch.release(), d.rows.release(), d.ascii.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
         d.offs.release(), d.rstart.release(), d.rlen.release();
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
@@ -681,6 +722,64 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
         ctx->timing.d2h_ms = std::max(ctx->timing.d2h_ms, d2h);
         ctx->timing.total_ms = std::max(ctx->timing.total_ms, tot);
     }
+    return MZ_OK;
+}
+
+int mz_pack_ascii(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out) {
+    if (!ctx || (n && (!ascii || !packed_out))) return MZ_ERR_BAD_ARG;
+    if (n == 0) return MZ_OK;
+    DevState& d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    ctx->timing = mz_timing{};
+    size_t nbytes = 0;
+    int rc = pack_on_device(d, ascii, n, &nbytes, &ctx->timing.kernel_launches);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(packed_out, d.in.p, (n + 3) / 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    return MZ_OK;
+}
+
+int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out) {
+    if (!ctx || !p || !out) return MZ_ERR_BAD_ARG;
+    int rc = mz_params_validate(p, n);
+    if (rc) return rc;
+    out->count = 0;
+    const uint32_t l = p->k + p->w - 1;
+    if (n < l) return MZ_OK;
+    if (!ascii || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
+    DevState& d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    ctx->timing = mz_timing{};
+    size_t nbytes = 0;
+    if ((rc = pack_on_device(d, ascii, n, &nbytes, &ctx->timing.kernel_launches))) return rc;
+    const uint64_t nwin = n - l + 1;
+    const uint32_t vw = p->value_bits / 64;
+    uint64_t cap = estimate_capacity(*p, nwin);
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if ((rc = d.pos.reserve(cap))) return rc;
+        if (p->want_sk && (rc = d.sk.reserve(cap))) return rc;
+        if (vw && (rc = d.val.reserve(cap * vw))) return rc;
+        mz::KArgs a{};
+        fill_input_args(a, *p, d.in.p, 0, 0, nbytes, nwin);
+        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = cap;
+        if ((rc = enqueue_run(d, *p, a, 0, nwin, &ctx->timing.kernel_launches))) return rc;
+        CK(cudaStreamSynchronize(d.stream));
+        if (!d.hs->overflow) break;
+        if (attempt == 1) {
+            g_last_error = "internal: exact-capacity re-run overflowed";
+            return MZ_ERR_CUDA;
+        }
+        cap = d.hs->count;
+    }
+    const uint64_t count = d.hs->count;
+    out->count = count;
+    if (count > out->capacity) return MZ_ERR_CAPACITY;
+    if (count) {
+        CK(cudaMemcpyAsync(out->pos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (p->want_sk) CK(cudaMemcpyAsync(out->sk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (vw) CK(cudaMemcpyAsync(out->val, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+    }
+    CK(cudaStreamSynchronize(d.stream));
     return MZ_OK;
 }
 

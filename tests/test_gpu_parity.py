@@ -378,3 +378,23 @@ def test_full_size_genome_properties(sm, oracle):
     del hs
     hv = torch.from_numpy(vals.view(np.int64)).cuda()
     assert torch.equal(hv, dv)
+
+
+def test_ascii_ingestion(sm, oracle):
+    """AsciiSeq input (src/test.rs:55-110 asserts ASCII == packed): device-side packing must
+    equal the host packing rule (c >> 1) & 3, and minimizers from ASCII equal those from packed."""
+    rng = np.random.default_rng(4)
+    for n in (0, 1, 15, 16, 17, 1000, 100_003):
+        s = bytes(rng.choice(np.frombuffer(b"ACGTacgt", dtype=np.uint8), n))
+        a = sm.AsciiSeq(s)
+        packed = a.pack()
+        ref = oracle.pack_ascii(s)
+        assert np.array_equal(packed.data[:(n + 3) // 4], ref[:(n + 3) // 4])
+        for (k, w, c) in ((5, 7, True), (21, 11, False)):
+            b = (sm.canonical_minimizers if c else sm.minimizers)(k, w)
+            pa, pp = sm.U32Vec(), sm.U32Vec()
+            va = b.run(a, pa).values_u64()
+            vp = b.run(packed, pp).values_u64()
+            assert pa == pp and np.array_equal(va, vp)
+            epos, _ = oracle.run(ref, 0, n, oracle.make_params(k, w, canonical=c))
+            assert np.array_equal(pa.array, epos)
