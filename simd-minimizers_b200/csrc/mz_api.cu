@@ -101,6 +101,8 @@ struct Plan {
     uint32_t NT = 128, S = 32;
     size_t smem = 0;
     uint32_t num_tiles = 0;
+    uint32_t grid = 0;            // generic kernel: persistent blocks
+    size_t ring_words = 0;        // generic kernel, huge w: per-block ring in global memory
 };
 
 uint32_t round_up(uint32_t x, uint32_t m) { return (x + m - 1) / m * m; }
@@ -118,22 +120,30 @@ int plan_generic(const DevState& d, const mz_params& p, uint64_t nwin, Plan* pl)
     uint32_t NT = 128;
     // shrink the block until a ring of w entries + 32 windows per thread fits
     while (NT >= 32 && generic_smem(NT, 32, p.w, lr) > budget) NT /= 2;
-    if (NT < 32) return MZ_ERR_UNSUPPORTED;
+    bool global_ring = false;
+    if (NT < 32) {  // w too large for a shared-memory ring: keep it in global memory (slow path)
+        NT = 64;
+        global_ring = true;
+    }
     // target ~4 tiles per SM, S in [32, 512], multiple of 32
     uint64_t target_tiles = (uint64_t)d.sm_count * 4;
     uint64_t s = (nwin + target_tiles * NT - 1) / (target_tiles * NT);
     uint32_t S = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s, 32), 512);
     S = round_up(S, 32);
-    while (S > 32 && generic_smem(NT, S, p.w, lr) > budget / 2) S -= 32;
+    const uint32_t wring = global_ring ? 0u : p.w;  // ring entries held in shared memory
+    while (S > 32 && generic_smem(NT, S, wring, lr) > budget / 2) S -= 32;
     if (S + p.w + 2 >= 65535) return MZ_ERR_UNSUPPORTED;
     pl->fast = false;
     pl->NT = NT;
     pl->S = S;
-    pl->smem = generic_smem(NT, S, p.w, lr);
+    pl->smem = generic_smem(NT, S, wring, lr);
+    pl->ring_words = global_ring ? (size_t)p.w * NT * (lr ? 2 : 1) : 0;
     uint64_t T = (uint64_t)NT * S;
     uint64_t tiles = (nwin + T - 1) / T;
     if (tiles == 0 || tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
     pl->num_tiles = (uint32_t)tiles;
+    const uint32_t bps = global_ring ? 2u : (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (pl->smem + 1024)));
+    pl->grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * bps);
     return MZ_OK;
 }
 
@@ -161,13 +171,13 @@ int launch_generic(const mz_params& p, const Plan& pl, const mz::KArgs& a, cudaS
     int rc;
     if (hc && lr) {
         if ((rc = set_smem(mz::mz_generic_kernel<true, true>, pl.smem))) return rc;
-        mz::mz_generic_kernel<true, true><<<pl.num_tiles, pl.NT, pl.smem, st>>>(a);
+        mz::mz_generic_kernel<true, true><<<pl.grid, pl.NT, pl.smem, st>>>(a);
     } else if (hc) {
         if ((rc = set_smem(mz::mz_generic_kernel<true, false>, pl.smem))) return rc;
-        mz::mz_generic_kernel<true, false><<<pl.num_tiles, pl.NT, pl.smem, st>>>(a);
+        mz::mz_generic_kernel<true, false><<<pl.grid, pl.NT, pl.smem, st>>>(a);
     } else {
         if ((rc = set_smem(mz::mz_generic_kernel<false, false>, pl.smem))) return rc;
-        mz::mz_generic_kernel<false, false><<<pl.num_tiles, pl.NT, pl.smem, st>>>(a);
+        mz::mz_generic_kernel<false, false><<<pl.grid, pl.NT, pl.smem, st>>>(a);
     }
     CK(cudaGetLastError());
     return MZ_OK;
@@ -190,6 +200,12 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
         a.list_cap = fp.list_cap;
     } else {
         rc = plan_generic(d, p, wend - wbeg, &pl);
+        a.scratch = nullptr;
+        if (!rc && pl.ring_words) {
+            if ((rc = d.rows.reserve(pl.ring_words * pl.grid))) return rc;
+            a.scratch = d.rows.p;
+            a.scratch_words_per_block = pl.ring_words;
+        }
     }
     if (rc) return rc;
     if ((rc = d.scratch.reserve(2 + (size_t)pl.num_tiles))) return rc;
@@ -848,6 +864,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         pl.S = S;
         pl.smem = generic_smem(NT, S, p->w, lr);
         pl.num_tiles = (uint32_t)tiles;
+        pl.grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (pl.smem + 1024))));
     }
 
     uint64_t cap = std::min<uint64_t>(estimate_capacity(*p, total_windows) + n_reads, total_windows);

@@ -23,7 +23,10 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
     const uint32_t nfw = (a.S + 31) / 32;
     uint16_t* rec = reinterpret_cast<uint16_t*>(flagw + (size_t)nfw * NT);
     // ring starts 8-byte aligned: S*NT*2 bytes with NT multiple of 32 is a multiple of 8
-    unsigned char* ring_raw = reinterpret_cast<unsigned char*>(rec + (size_t)a.S * NT);
+    // very large w: the ring does not fit shared memory and lives in a per-block global region
+    unsigned char* ring_raw = a.scratch
+        ? reinterpret_cast<unsigned char*>(a.scratch + (size_t)blockIdx.x * a.scratch_words_per_block)
+        : reinterpret_cast<unsigned char*>(rec + (size_t)a.S * NT);
     uint2* ring2 = reinterpret_cast<uint2*>(ring_raw);
     uint32_t* ring1 = reinterpret_cast<uint32_t*>(ring_raw);
 
@@ -36,7 +39,6 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
         tab[tid] = make_uint2(dfw, drc);
     }
     if (tid == 0) {
-        misc[0] = atomicAdd(a.ticket, 1u);
         // hash state of the virtual all-'A' k-mer that precedes every segment
         uint32_t fa = 0, ca = 0;
         for (uint32_t j = 0; j < k; j++) {
@@ -46,8 +48,12 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
         misc[1] = fa;
         misc[2] = ca;
     }
+    for (;;) {  // persistent blocks: one tile per iteration
+    __syncthreads();
+    if (tid == 0) misc[0] = atomicAdd(a.ticket, 1u);
     __syncthreads();
     const uint32_t tile = misc[0];
+    if (tile >= a.num_tiles) break;
     const Segment sg = make_segment(a, tile, tid);
 
     uint32_t cnt = 0;
@@ -149,6 +155,7 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
                    jv = q * 32u + bit;
                    d = (uint32_t)rec[jv * NT + tid] - (jv + sg.has_prev);
                });
+    }  // persistent loop
 }
 
 }  // namespace mz

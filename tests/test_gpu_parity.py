@@ -398,3 +398,15 @@ def test_ascii_ingestion(sm, oracle):
             assert pa == pp and np.array_equal(va, vp)
             epos, _ = oracle.run(ref, 0, n, oracle.make_params(k, w, canonical=c))
             assert np.array_equal(pa.array, epos)
+
+
+def test_very_large_w(sm, oracle):
+    """w up to the reference's limit (w < 2^15, src/sliding_min.rs:92-95): the generic kernel keeps
+    its two-stacks ring in global memory when it no longer fits shared memory."""
+    packed = oracle.synth_packed(21, 200_000)
+    for (k, w, c, n) in ((5, 801, True, 60_000), (8, 2000, False, 50_000), (3, 32767, True, 150_000),
+                         (31, 1000, True, 20_000), (7, 4097, False, 4096 + 7 - 1)):
+        if c and (k + w - 1) % 2 == 0:
+            w += 1
+        for mode in (0, 1):
+            _check_case(sm, oracle, packed, 1, n, k, w, c, mode)
