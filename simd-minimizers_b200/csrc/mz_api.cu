@@ -80,6 +80,7 @@ struct DevState {
     DevBuf<uint64_t> offs;  // batch CSR offsets
     DevBuf<uint64_t> rstart;
     DevBuf<uint32_t> rlen;
+    DevBuf<uint32_t> pread, pwin;  // batch pieces of long reads
     HostScalars* hs = nullptr;
 };
 
@@ -540,7 +541,7 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         cudaSetDevice(d.device);
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.scratch.release(), d.rows.release(), d.ascii.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
-        d.offs.release(), d.rstart.release(), d.rlen.release();
+        d.offs.release(), d.rstart.release(), d.rlen.release(), d.pread.release(), d.pwin.release();
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
         if (d.hs) cudaFreeHost(d.hs);
@@ -829,19 +830,54 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         return MZ_OK;
     }
     if (!packed || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
-    const uint32_t S = max_len - l + 1;  // windows of the longest read: one read per thread
+    const uint32_t S_full = max_len - l + 1;  // windows of the longest read
     const uint32_t vw = p->value_bits / 64;
     DevState& d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
     ctx->timing = mz_timing{};
 
-    // geometry: fast kernel (tile = 32 reads) when the per-thread record fits, else generic
+    // Geometry.  A thread handles one read when the longest read fits the per-thread record of
+    // the chosen kernel; otherwise reads are cut into pieces of S windows (each piece a thread,
+    // seam rule as everywhere: one extra window on the left seeds the dedup comparison).
     Plan pl;
     mz::FastPlan fp;
-    bool fast = p->w <= mz::FAST_MAX_W && !(p->hash_canonical && !p->strand_tiebreak) &&
-                mz::fast_smem(S, p->w, mz::fast_list_cap(S, *p)) <= 56 * 1024 && (uint64_t)S + p->w + 2 < 65535;
+    const bool lr = p->strand_tiebreak != 0;
+    const bool fast = p->w <= mz::FAST_MAX_W && !(p->hash_canonical && !p->strand_tiebreak);
+    uint32_t S_cap;
     if (fast) {
-        const uint64_t tiles = (n_reads + 31) / 32;
+        S_cap = 288;
+        while (S_cap > 16 && mz::fast_smem(S_cap, p->w, mz::fast_list_cap(S_cap, *p)) > 56 * 1024) S_cap -= 16;
+    } else {
+        const size_t budget = std::min<size_t>(d.smem_optin, 200 * 1024);
+        pl.NT = 128;
+        while (pl.NT >= 32 && generic_smem(pl.NT, 32, p->w, lr) > budget) pl.NT /= 2;
+        if (pl.NT < 32) {
+            g_last_error = "mz_run_batch: w too large for the batch kernels";
+            return MZ_ERR_UNSUPPORTED;
+        }
+        S_cap = 512;
+        while (S_cap > 32 && generic_smem(pl.NT, S_cap, p->w, lr) > budget / 2) S_cap -= 32;
+    }
+    const uint32_t S = std::min(S_full, S_cap);
+    if ((uint64_t)S + p->w + 2 >= 65535) return MZ_ERR_UNSUPPORTED;
+    std::vector<uint32_t> piece_read, piece_win0;
+    uint64_t n_units = n_reads;  // threads needed
+    if (S_full > S_cap) {
+        if (n_reads >= (1ull << 32)) return MZ_ERR_UNSUPPORTED;
+        for (uint64_t r = 0; r < n_reads; r++) {
+            const uint32_t len = read_len_bp ? read_len_bp[r] : fixed_len_bp;
+            const uint32_t nw = len >= l ? len - l + 1 : 0;
+            uint32_t w0 = 0;
+            do {  // every read owns at least one piece (it writes the read's CSR offset)
+                piece_read.push_back((uint32_t)r);
+                piece_win0.push_back(w0);
+                w0 += S;
+            } while (w0 < nw);
+        }
+        n_units = piece_read.size();
+    }
+    if (fast) {
+        const uint64_t tiles = (n_units + 31) / 32;
         if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
         fp.S = S;
         fp.num_tiles = (uint32_t)tiles;
@@ -850,19 +886,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         fp.list_cap = mz::fast_list_cap(S, *p);
         pl.num_tiles = fp.num_tiles;
     } else {
-        const bool lr = p->strand_tiebreak != 0;
-        uint32_t NT = 128;
-        const size_t budget = std::min<size_t>(d.smem_optin, 200 * 1024);
-        while (NT >= 32 && generic_smem(NT, S, p->w, lr) > budget) NT /= 2;
-        if (NT < 32 || (uint64_t)S + p->w + 2 >= 65535) {
-            g_last_error = "mz_run_batch: reads too long for the one-read-per-thread batch kernels";
-            return MZ_ERR_UNSUPPORTED;
-        }
-        const uint64_t tiles = (n_reads + NT - 1) / NT;
+        const uint64_t tiles = (n_units + pl.NT - 1) / pl.NT;
         if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
-        pl.NT = NT;
         pl.S = S;
-        pl.smem = generic_smem(NT, S, p->w, lr);
+        pl.smem = generic_smem(pl.NT, S, p->w, lr);
         pl.num_tiles = (uint32_t)tiles;
         pl.grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (pl.smem + 1024))));
     }
@@ -874,8 +901,16 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         if ((rc = d.rstart.reserve(n_reads))) return rc;
         if ((rc = d.rlen.reserve(n_reads))) return rc;
     }
+    if (!piece_read.empty()) {
+        if ((rc = d.pread.reserve(n_units))) return rc;
+        if ((rc = d.pwin.reserve(n_units))) return rc;
+    }
     CK(cudaEventRecord(d.ev[0], d.stream));
     CK(cudaMemcpyAsync(d.in.p, packed, packed_bytes, cudaMemcpyHostToDevice, d.stream));
+    if (!piece_read.empty()) {
+        CK(cudaMemcpyAsync(d.pread.p, piece_read.data(), n_units * 4, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d.pwin.p, piece_win0.data(), n_units * 4, cudaMemcpyHostToDevice, d.stream));
+    }
     if (read_start_bp) {
         CK(cudaMemcpyAsync(d.rstart.p, read_start_bp, n_reads * 8, cudaMemcpyHostToDevice, d.stream));
         CK(cudaMemcpyAsync(d.rlen.p, read_len_bp, n_reads * 4, cudaMemcpyHostToDevice, d.stream));
@@ -900,7 +935,9 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         a.ticket = reinterpret_cast<uint32_t*>(d.scratch.p + 1);
         a.overflow = a.ticket + 1;
         a.tile_state = d.scratch.p + 2;
-        a.n_reads = n_reads;
+        a.n_reads = n_units;
+        a.piece_read = piece_read.empty() ? nullptr : d.pread.p;
+        a.piece_win0 = piece_read.empty() ? nullptr : d.pwin.p;
         a.read_start_bp = read_start_bp ? d.rstart.p : nullptr;
         a.read_len_bp = read_start_bp ? d.rlen.p : nullptr;
         a.stride_bits = stride_bytes * 8;

@@ -45,6 +45,9 @@ struct KArgs {
     uint64_t stride_bits;            // fixed stride between reads, in bits
     uint32_t fixed_len_bp;
     uint64_t* out_offsets;           // CSR offsets, n_reads + 1
+    // long reads: a thread handles one PIECE (S windows) of a read; n_reads then counts pieces
+    const uint32_t* piece_read;      // read index of every piece (null: piece == read)
+    const uint32_t* piece_win0;      // first window of the piece inside its read
 };
 
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, uint32_t r) {

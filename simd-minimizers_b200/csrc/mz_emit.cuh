@@ -38,18 +38,27 @@ __device__ __forceinline__ Segment make_segment_nt(const KArgs& a, uint32_t tile
         s.win_base = j0;
         s.first_always = (j0 == 0);
     } else {
-        uint64_t r = (uint64_t)tile * NT + tid;
+        // batch mode: thread = read, or = piece of S windows of a long read
+        const uint64_t pi = (uint64_t)tile * NT + tid;
         s.has_prev = 0;
         s.first_always = 1;
         s.pos_base = 0;
         s.win_base = 0;
         s.nvalid = 0;
         s.bit0 = 0;
-        if (r < a.n_reads) {
-            uint64_t startbits = a.read_start_bp ? 2 * a.read_start_bp[r] : r * a.stride_bits;
-            uint32_t len = a.read_len_bp ? a.read_len_bp[r] : a.fixed_len_bp;
-            s.bit0 = (uint64_t)((int64_t)startbits + a.bitbias);
-            s.nvalid = len >= a.l ? len - a.l + 1 : 0;
+        if (pi < a.n_reads) {
+            const uint64_t r = a.piece_read ? a.piece_read[pi] : pi;
+            const uint32_t win0 = a.piece_read ? a.piece_win0[pi] : 0u;
+            const uint64_t startbits = a.read_start_bp ? 2 * a.read_start_bp[r] : r * a.stride_bits;
+            const uint32_t len = a.read_len_bp ? a.read_len_bp[r] : a.fixed_len_bp;
+            const uint32_t nw = len >= a.l ? len - a.l + 1 : 0;
+            const uint32_t left = nw > win0 ? nw - win0 : 0;
+            s.nvalid = left < a.S ? left : a.S;
+            s.has_prev = (win0 > 0 && a.mode == MODE_MINIMIZER) ? 1u : 0u;
+            s.first_always = (win0 == 0);
+            s.pos_base = win0 - s.has_prev;
+            s.win_base = win0;
+            s.bit0 = (uint64_t)((int64_t)(startbits + 2ull * s.pos_base) + a.bitbias);
         }
     }
     return s;
@@ -57,6 +66,18 @@ __device__ __forceinline__ Segment make_segment_nt(const KArgs& a, uint32_t tile
 
 __device__ __forceinline__ Segment make_segment(const KArgs& a, uint32_t tile, uint32_t tid) {
     return make_segment_nt(a, tile, tid, blockDim.x);
+}
+
+// CSR end offset of a read, written by the thread that owns the read's last piece.
+__device__ __forceinline__ void write_csr_offset(const KArgs& a, uint64_t pi, unsigned long long end) {
+    if (pi >= a.n_reads) return;
+    uint64_t r = pi;
+    if (a.piece_read) {
+        r = a.piece_read[pi];
+        if (pi + 1 < a.n_reads && a.piece_read[pi + 1] == r) return;  // not the last piece
+    }
+    a.out_offsets[r + 1] = end;
+    if (r == 0) a.out_offsets[0] = 0;
 }
 
 constexpr uint32_t EMIT_CHUNK = 2048;  // entries staged per round
@@ -98,13 +119,7 @@ __device__ __forceinline__ void emit_phase(const KArgs& a, const Segment& sg, ui
     const unsigned long long gbase = s_gbase;
     const bool ovf = gbase + total > a.cap;
     if (ovf && tid == 0) *a.overflow = 1u;
-    if (a.n_reads != 0) {
-        uint64_t r = (uint64_t)tile * NT + tid;
-        if (r < a.n_reads) {
-            a.out_offsets[r + 1] = gbase + toff + cnt;
-            if (r == 0) a.out_offsets[0] = 0;
-        }
-    }
+    if (a.n_reads != 0) write_csr_offset(a, (uint64_t)tile * NT + tid, gbase + toff + cnt);
     if (ovf || total == 0) return;
 
     const bool minim = a.mode == MODE_MINIMIZER;

@@ -407,13 +407,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
         if (lane == 0 && tile_e == a.num_tiles - 1) *a.count_out = gbase + total;
         const bool ovf = gbase + total > a.cap;
         if (ovf && lane == 0) *a.overflow = 1u;
-        if (a.n_reads != 0) {
-            const uint64_t r = (uint64_t)tile_e * 32u + lane;
-            if (r < a.n_reads) {
-                a.out_offsets[r + 1] = gbase + inc_e;
-                if (r == 0) a.out_offsets[0] = 0;
-            }
-        }
+        if (a.n_reads != 0) write_csr_offset(a, (uint64_t)tile_e * 32u + lane, gbase + inc_e);
         if (!ovf && total != 0) {
 
         // Tile-uniform addressing (32-bit offsets from the tile's first thread).
@@ -498,8 +492,8 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                 } else {
                     const Segment og = make_segment_nt(a, tile_e, t2, 32u);
                     const unsigned long long oi = gbase + cbase + x;
-                    a.pos[oi] = local;
-                    if (a.want_sk) a.sk[oi] = jl;
+                    a.pos[oi] = (uint32_t)og.pos_base + local;
+                    if (a.want_sk) a.sk[oi] = (uint32_t)og.win_base + (jl - og.has_prev);
                     if (a.value_bits == 64) {
                         a.val[oi] = kmer_value_u64(a, og.bit0 + 2ull * local, a.val_len, canon_val);
                     } else if (a.value_bits == 128) {

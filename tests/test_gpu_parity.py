@@ -410,3 +410,29 @@ def test_very_large_w(sm, oracle):
             w += 1
         for mode in (0, 1):
             _check_case(sm, oracle, packed, 1, n, k, w, c, mode)
+
+
+def test_batch_long_reads_are_cut_into_pieces(sm, oracle):
+    """Reads longer than the per-thread record are processed as pieces of S windows; the result
+    must still equal the per-read reference call (dedup across piece seams, CSR per read)."""
+    rng = np.random.default_rng(10)
+    lens = np.array([0, 20, 150, 289, 290, 318, 319, 320, 1000, 5000, 37, 12_345, 600, 49, 48], dtype=np.uint32)
+    lens = np.concatenate([lens, rng.integers(0, 3000, 40).astype(np.uint32)])
+    starts = np.zeros(len(lens), dtype=np.uint64)
+    cur = 1
+    for i, n in enumerate(lens):
+        starts[i] = cur
+        cur += int(n) + int(rng.integers(0, 5))
+    packed = oracle.synth_packed(55, cur + 64)
+    for (k, w, c, mode) in ((31, 19, True, 0), (21, 11, False, 0), (15, 9, True, 1), (9, 41, False, 0), (5, 3, False, 2)):
+        b = _builder(sm, k, w, c, mode)
+        sk = sm.U32Vec()
+        bb = b.super_kmers(sk) if mode == 0 else b
+        offs, pos, sks, vals = bb.run_batch(packed, starts=starts, lens=lens)
+        eo, ep, es, ev = _oracle_batch(oracle, packed, starts, lens, k, w, c, mode, mode == 0)
+        assert np.array_equal(offs, eo), (k, w, c, mode)
+        assert np.array_equal(pos, ep), (k, w, c, mode)
+        if mode == 0:
+            assert np.array_equal(sks, es), (k, w, c, mode)
+        if ev is not None:
+            assert np.array_equal(vals, ev), (k, w, c, mode)
