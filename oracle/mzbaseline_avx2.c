@@ -271,7 +271,19 @@ typedef struct {
     uint32_t *pos, *sk;
     uint64_t* val;
     int use_avx2;
+    uint64_t skip, dst, ncopy;
+    uint32_t *pos_out, *sk_out;
+    uint64_t* val_out;
 } bjob;
+
+static void* bcopy_worker(void* arg) {
+    bjob* j = (bjob*)arg;
+    if (!j->ncopy) return NULL;
+    memcpy(j->pos_out + j->dst, j->pos + j->skip, 4 * j->ncopy);
+    if (j->sk_out) memcpy(j->sk_out + j->dst, j->sk + j->skip, 4 * j->ncopy);
+    if (j->val_out) memcpy(j->val_out + j->dst, j->val + j->skip, 8 * j->ncopy);
+    return NULL;
+}
 
 static void* bworker(void* arg) {
     bjob* j = (bjob*)arg;
@@ -322,25 +334,32 @@ uint64_t mzb_run_mt(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_p
         for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, bworker, &jobs[t]);
         for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     }
+    /* ordered concatenation, in parallel: offsets first (seam rule), then one copy per thread */
     uint64_t m = 0;
+    uint32_t last = 0;
+    int have_last = 0;
     for (int t = 0; t < threads && ok; t++) {
         bjob* j = &jobs[t];
+        j->skip = 0, j->dst = m, j->ncopy = 0;
         if (j->wb == j->we) continue;
         if (j->count == (uint64_t)-1) {
             ok = 0;
             break;
         }
         /* thread seam: same flatten rule (only the AVX2 path emits its first window blindly) */
-        const uint64_t skip = (use_avx2 && m > 0 && j->count > 0 && j->pos[0] == pos_out[m - 1]) ? 1 : 0;
-        const uint64_t c = j->count - skip;
-        if (m + c > cap) {
+        j->skip = (use_avx2 && have_last && j->count > 0 && j->pos[0] == last) ? 1 : 0;
+        j->ncopy = j->count - j->skip;
+        if (m + j->ncopy > cap) {
             ok = 0;
             break;
         }
-        memcpy(pos_out + m, j->pos + skip, 4 * c);
-        if (sk_out) memcpy(sk_out + m, j->sk + skip, 4 * c);
-        if (val_out) memcpy(val_out + m, j->val + skip, 8 * c);
-        m += c;
+        if (j->count) last = j->pos[j->count - 1], have_last = 1;
+        j->pos_out = pos_out, j->sk_out = sk_out, j->val_out = val_out;
+        m += j->ncopy;
+    }
+    if (ok) {
+        for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, bcopy_worker, &jobs[t]);
+        for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
     }
     for (int t = 0; t < threads; t++) free(jobs[t].pos), free(jobs[t].sk), free(jobs[t].val);
     free(jobs);
