@@ -436,3 +436,20 @@ def test_batch_long_reads_are_cut_into_pieces(sm, oracle):
             assert np.array_equal(sks, es), (k, w, c, mode)
         if ev is not None:
             assert np.array_equal(vals, ev), (k, w, c, mode)
+
+
+def test_degenerate_and_dense_outputs_at_scale(sm, oracle):
+    """Worst cases for the ordered compaction at a size that spans many tiles and chunks:
+    homopolymer (every window emits, leftmost == window start), short periods (ties in every
+    window: the strand fix-up runs in every block), w=1 (density 1) and w=2.  The capacity
+    estimate is exceeded on purpose, so the exact-size re-run path is exercised too."""
+    n = 20_000_000
+    pats = {"polyA": b"A", "polyG": b"G", "AC": b"AC", "ACGTT": b"ACGTT"}
+    for name, pat in pats.items():
+        s = (pat * (n // len(pat) + 1))[:n]
+        packed = oracle.pack_ascii(s)
+        for (k, w, c, mode) in ((31, 19, True, 0), (21, 11, False, 0), (31, 11, True, 1)):
+            _check_case(sm, oracle, packed, 0, n, k, w, c, mode)
+    rnd = oracle.synth_packed(9, n)
+    for (k, w, c, mode) in ((5, 1, True, 0), (8, 2, False, 0), (31, 1, True, 1), (9, 3, True, 2)):
+        _check_case(sm, oracle, rnd, 0, n, k, w, c, mode)
