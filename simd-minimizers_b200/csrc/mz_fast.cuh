@@ -31,9 +31,13 @@ constexpr uint32_t FAST_NT = 128;  // threads per block (compile-time: scratch s
 // for every tile the persistent block processes).  Row r, thread t -> word scratch[r*NT + t]:
 //   rows (b*WQ + q)   low bytes of the selected positions of windows 4q..4q+3 of van-Herk block b
 // The flag word of block b (bit t <-> window ending at element bW+t) stays in shared memory.
-__host__ __device__ constexpr uint32_t fast_wq(uint32_t W) { return (W + 3) / 4; }
+// Small windows: several van-Herk blocks (B of them, B*W <= 32 k-mers) share one loop iteration, so
+// the per-iteration ingest/record overhead is amortised over ~32 k-mers for every W.
+__host__ __device__ constexpr uint32_t fast_b(uint32_t W) { return W <= 16 ? 32 / W : 1; }
+__host__ __device__ constexpr uint32_t fast_sb(uint32_t W) { return fast_b(W) * W; }
+__host__ __device__ constexpr uint32_t fast_wq(uint32_t W) { return (fast_sb(W) + 3) / 4; }
 __host__ __device__ inline uint32_t fast_nb(uint32_t S, uint32_t W) {
-    return (S + 1 + (W - 1) + W - 1) / W;  // elements = S + has_prev + W - 1
+    return (S + 1 + (W - 1) + fast_sb(W) - 1) / fast_sb(W);  // k-mers = S + has_prev + W - 1
 }
 // scratch words per WARP (a warp is an autonomous worker: tile = 32 threads x S windows)
 inline size_t fast_scratch_words(uint32_t S, uint32_t W) {
@@ -101,7 +105,9 @@ __device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
 template <int W, bool HC, bool LR, bool SYNC>
 __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
-    constexpr int WQ = (W + 3) / 4;
+    constexpr int B = (int)fast_b(W);    // van-Herk blocks per loop iteration
+    constexpr int SB = B * W;            // k-mers per loop iteration (<= 32)
+    constexpr int WQ = (SB + 3) / 4;     // record words per iteration
     constexpr uint32_t NT = FAST_NT;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -160,7 +166,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
         if (sg.nvalid) {
             uint32_t fw = misc[1], rc = misc[2];
             const uint32_t nelem = sg.nvalid + sg.has_prev + (W - 1);
-            NB = (nelem + W - 1) / W;
+            NB = (nelem + SB - 1) / SB;
             // first/last valid window-end element: e = jl + W - 1, jl in [has_prev, has_prev + nvalid)
             const uint32_t e_lo = sg.has_prev + (W - 1), e_hi = e_lo + sg.nvalid;
 
@@ -197,15 +203,15 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             uint32_t pin = sh0 + 32u + 2u * (k - 1);  // bit position (+32) of the entering stream
             uint32_t pout = sh0 + 30u;                // bit position (+32) of the leaving stream
             // may any (pre)fetch of this thread touch a word past the end of the buffer?
-            const bool clampd = ((pin + 2u * (NB + 1) * W) >> 5) + 2u > wlim;
+            const bool clampd = ((pin + 2u * (NB + 1) * SB) >> 5) + 2u > wlim;
             auto ldw = [&](uint32_t wl1) -> uint32_t {  // wl1 = word offset + 1 (virtual word 0)
                 if (wl1 == 0) return 0u;
                 uint32_t wl = wl1 - 1;
                 if (clampd) wl = min(wl, wlim);
                 return __ldg(wbase + wl);
             };
-            uint32_t iw0 = ldw(pin >> 5), iw1 = ldw((pin >> 5) + 1), iw2 = W > 16 ? ldw((pin >> 5) + 2) : 0u;
-            uint32_t ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1), ow2 = W > 16 ? ldw((pout >> 5) + 2) : 0u;
+            uint32_t iw0 = ldw(pin >> 5), iw1 = ldw((pin >> 5) + 1), iw2 = SB > 16 ? ldw((pin >> 5) + 2) : 0u;
+            uint32_t ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1), ow2 = SB > 16 ? ldw((pout >> 5) + 2) : 0u;
             ow0 &= ~(3u << (pout & 31u));  // element 0 leaves the virtual 'A'
 
             uint32_t RL[W], RR[W];
@@ -215,35 +221,44 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             uint32_t* sp = scr;
 
             for (uint32_t b = 0; b < NB; b++) {
-                const uint32_t eb = b * W;
+                const uint32_t eb = b * SB;
                 const uint32_t shi = pin & 31u, sho = pout & 31u;
-                const uint32_t x0 = __funnelshift_r(iw0, iw1, shi), x1 = W > 16 ? __funnelshift_r(iw1, iw2, shi) : 0u;
-                const uint32_t y0 = __funnelshift_r(ow0, ow1, sho), y1 = W > 16 ? __funnelshift_r(ow1, ow2, sho) : 0u;
+                const uint32_t x0 = __funnelshift_r(iw0, iw1, shi), x1 = SB > 16 ? __funnelshift_r(iw1, iw2, shi) : 0u;
+                const uint32_t y0 = __funnelshift_r(ow0, ow1, sho), y1 = SB > 16 ? __funnelshift_r(ow1, ow2, sho) : 0u;
                 // prefetch the next block's words (consumed ~W*30 instructions later)
-                pin += 2u * W;
-                pout += 2u * W;
+                pin += 2u * SB;
+                pout += 2u * SB;
                 if (!clampd) {
                     const uint32_t* pi = wbase + (pin >> 5) - 1;
                     const uint32_t* po = wbase + (pout >> 5) - 1;
                     iw0 = __ldg(pi), iw1 = __ldg(pi + 1);
                     ow0 = __ldg(po), ow1 = __ldg(po + 1);
-                    if (W > 16) iw2 = __ldg(pi + 2), ow2 = __ldg(po + 2);
+                    if (SB > 16) iw2 = __ldg(pi + 2), ow2 = __ldg(po + 2);
                 } else {
                     iw0 = ldw(pin >> 5), iw1 = ldw((pin >> 5) + 1);
                     ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1);
-                    if (W > 16) iw2 = ldw((pin >> 5) + 2), ow2 = ldw((pout >> 5) + 2);
-                }
-                uint32_t N[4];
-                N[0] = (x0 & 0x0F0F0F0Fu) | ((y0 << 4) & 0xF0F0F0F0u);
-                N[1] = ((x0 >> 4) & 0x0F0F0F0Fu) | (y0 & 0xF0F0F0F0u);
-                if (W > 16) {
-                    N[2] = (x1 & 0x0F0F0F0Fu) | ((y1 << 4) & 0xF0F0F0F0u);
-                    N[3] = ((x1 >> 4) & 0x0F0F0F0Fu) | (y1 & 0xF0F0F0F0u);
+                    if (SB > 16) iw2 = ldw((pin >> 5) + 2), ow2 = ldw((pout >> 5) + 2);
                 }
                 uint32_t preL = 0, preR = 0, bf = 0, tacc = 0, lastR = 0;
                 uint32_t accL[WQ], accR[WQ];
 #pragma unroll
                 for (int q = 0; q < WQ; q++) accL[q] = 0, accR[q] = 0;
+#pragma unroll
+                for (int j = 0; j < B; j++) {  // van-Herk block j of this iteration
+                const int o = j * W;           // its first k-mer inside the iteration
+                // this block's 2W bits of both streams, interleaved: byte = (in,in,out,out)
+                uint32_t xs0 = x0, xs1 = x1, ys0 = y0, ys1 = y1;
+                if (o != 0) {  // B > 1 implies W <= 16: one 32-bit word per stream is enough
+                    xs0 = 2 * o < 32 ? __funnelshift_r(x0, x1, 2 * o) : (x1 >> ((2 * o - 32) & 31));
+                    ys0 = 2 * o < 32 ? __funnelshift_r(y0, y1, 2 * o) : (y1 >> ((2 * o - 32) & 31));
+                }
+                uint32_t N[4];
+                N[0] = (xs0 & 0x0F0F0F0Fu) | ((ys0 << 4) & 0xF0F0F0F0u);
+                N[1] = ((xs0 >> 4) & 0x0F0F0F0Fu) | (ys0 & 0xF0F0F0F0u);
+                if (W > 16) {
+                    N[2] = (xs1 & 0x0F0F0F0Fu) | ((ys1 << 4) & 0xF0F0F0F0u);
+                    N[3] = ((xs1 >> 4) & 0x0F0F0F0Fu) | (ys1 & 0xF0F0F0F0u);
+                }
                 // Two k-mers per step: one table load gives both hashes; the prefix minimum and
                 // the first window of the pair use the 3-input VIMNMX3.
 #pragma unroll
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                         }
                     }
                     // positions: eb + t on the FMA pipe (IMAD with an opaque 1), the ALU pipe is the bottleneck
-                    const uint32_t pos0 = imad(eb, one, t), pos1 = imad(eb, one, t + 1);
+                    const uint32_t pos0 = imad(eb, one, o + t), pos1 = imad(eb, one, o + t + 1);
                     const uint32_t le0 = (h0 & 0xffff0000u) | pos0, le1 = (h1 & 0xffff0000u) | pos1;
                     uint32_t res0, res1 = 0, mR0 = 0, mR1 = 0;
                     {
@@ -309,31 +324,31 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                         RR[t] = re0;
                         if (two) RR[t + 1] = re1;
                         tacc |= res0 ^ mR0;  // low half != 0  <=>  leftmost != rightmost
-                        accR[t >> 2] = put_byte(accR[t >> 2], mR0, t & 3);
+                        accR[(o + t) >> 2] = put_byte(accR[(o + t) >> 2], mR0, (o + t) & 3);
                         if (two) {
                             tacc |= res1 ^ mR1;
-                            accR[(t + 1) >> 2] = put_byte(accR[(t + 1) >> 2], mR1, (t + 1) & 3);
+                            accR[(o + t + 1) >> 2] = put_byte(accR[(o + t + 1) >> 2], mR1, (o + t + 1) & 3);
                         }
-                        if (t == W - 1) lastR = mR0;
-                        if (t + 1 == W - 1) lastR = mR1;
+                        if (o + t == SB - 1) lastR = mR0;
+                        if (o + t + 1 == SB - 1) lastR = mR1;
                     }
                     if (SYNC) {
                         const uint32_t d0 = pos0 - (res0 & 0xffffu);
-                        if (d0 == so1 || d0 == so2) bf |= 1u << t;
+                        if (d0 == so1 || d0 == so2) bf |= 1u << (o + t);
                         if (two) {
                             const uint32_t d1 = pos1 - (res1 & 0xffffu);
-                            if (d1 == so1 || d1 == so2) bf |= 1u << (t + 1);
+                            if (d1 == so1 || d1 == so2) bf |= 1u << (o + t + 1);
                         }
                     } else {
-                        or_if_ne(bf, res0, prev, 1u << t);
+                        or_if_ne(bf, res0, prev, 1u << (o + t));
                         prev = res0;
                         if (two) {
-                            or_if_ne(bf, res1, prev, 1u << (t + 1));
+                            or_if_ne(bf, res1, prev, 1u << (o + t + 1));
                             prev = res1;
                         }
                     }
-                    accL[t >> 2] = put_byte(accL[t >> 2], res0, t & 3);
-                    if (two) accL[(t + 1) >> 2] = put_byte(accL[(t + 1) >> 2], res1, (t + 1) & 3);
+                    accL[(o + t) >> 2] = put_byte(accL[(o + t) >> 2], res0, (o + t) & 3);
+                    if (two) accL[(o + t + 1) >> 2] = put_byte(accL[(o + t + 1) >> 2], res1, (o + t + 1) & 3);
                 }
                 // suffix minima of this block (slot 0 is never needed)
 #pragma unroll
@@ -341,20 +356,21 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     RL[q] = min(RL[q], RL[q + 1]);
                     if (LR) RR[q] = max(RR[q], RR[q + 1]);
                 }
+                }  // van-Herk blocks of this iteration
                 if (LR && (tacc & 0xffffu) != 0u) {
                     // cold: some window of this block has leftmost != rightmost.  Apply the strand
                     // rule to those windows and rebuild the block's flags from the position bytes.
                     bf = 0;
                     uint32_t pl = prevlow;
 #pragma unroll
-                    for (int t = 0; t < W; t++) {
+                    for (int t = 0; t < SB; t++) {
                         uint32_t cur = get_byte(accL[t >> 2], t & 3);
                         const uint32_t rgt = get_byte(accR[t >> 2], t & 3);
                         if (cur != rgt && eb + t >= (uint32_t)(W - 1)) {
                             if (!window_prefers_left(wbase, sh0, wlim, 2u * (eb + t - (W - 1)), a.l)) {
                                 cur = rgt;
                                 accL[t >> 2] = put_byte(accL[t >> 2], rgt, t & 3);
-                                if (t == W - 1) prev = lastR ^ 0xffff0000u;
+                                if (t == SB - 1) prev = lastR ^ 0xffff0000u;
                             }
                         }
                         if (SYNC) {
@@ -366,15 +382,15 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                         }
                     }
                 }
-                prevlow = get_byte(accL[(W - 1) >> 2], (W - 1) & 3);
+                prevlow = get_byte(accL[(SB - 1) >> 2], (SB - 1) & 3);
                 // keep flags of valid windows only: bit t <-> window-end element eb + t
                 // (only the first and last blocks of a segment can hold invalid windows)
-                if (eb < e_lo + 1u || eb + W > e_hi) {
-                    const uint32_t lo = e_lo > eb ? min(e_lo - eb, (uint32_t)W) : 0u;
-                    const uint32_t hi = e_hi > eb ? min(e_hi - eb, (uint32_t)W) : 0u;
+                if (eb < e_lo + 1u || eb + SB > e_hi) {
+                    const uint32_t lo = e_lo > eb ? min(e_lo - eb, (uint32_t)SB) : 0u;
+                    const uint32_t hi = e_hi > eb ? min(e_hi - eb, (uint32_t)SB) : 0u;
                     const uint32_t mhi = hi >= 32u ? 0xffffffffu : ((1u << hi) - 1u);
                     const uint32_t mlo = lo >= 32u ? 0xffffffffu : ((1u << lo) - 1u);
-                    if (!SYNC && sg.first_always && e_lo >= eb && e_lo < eb + W) bf |= 1u << (e_lo - eb);
+                    if (!SYNC && sg.first_always && e_lo >= eb && e_lo < eb + SB) bf |= 1u << (e_lo - eb);
                     bf &= mhi & ~mlo;
                 }
                 flp[b * 32] = bf;
@@ -434,7 +450,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                 }
                 const uint32_t bit = (uint32_t)__ffs(f) - 1u;
                 f &= f - 1u;
-                list[toff + produced - cbase] = (lane << 16) | (bq * W + bit);
+                list[toff + produced - cbase] = (lane << 16) | (bq * SB + bit);
                 produced++;
             }
             __syncwarp();
@@ -445,7 +461,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
 #pragma unroll 4
             for (uint32_t x = lane; x < nent; x += 32) {
                 const uint32_t dsc = list[x];
-                const uint32_t t2 = dsc >> 16, e = dsc & 0xffffu, b2 = e / W, bit2 = e - b2 * W;
+                const uint32_t t2 = dsc >> 16, e = dsc & 0xffffu, b2 = e / SB, bit2 = e - b2 * SB;
                 const uint32_t wv = __ldcg(scr0 + (size_t)(b2 * WQ + (bit2 >> 2)) * 32 + t2);
                 const uint32_t lowb = (wv >> (8u * (bit2 & 3u))) & 0xffu;
                 const uint32_t jl = e - (W - 1);  // local window index of the owner
