@@ -842,7 +842,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     Plan pl;
     mz::FastPlan fp;
     const bool lr = p->strand_tiebreak != 0;
-    const bool fast = p->w <= mz::FAST_MAX_W && !(p->hash_canonical && !p->strand_tiebreak);
+    const bool fast = p->w <= mz::FAST_MAX_W;
     uint32_t S_cap;
     if (fast) {
         S_cap = 288;

@@ -538,7 +538,6 @@ struct FastPlan {
 // Geometry for the fast kernel; returns false when (k, w, ...) is outside its domain.
 inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan* pl) {
     if (p.w > FAST_MAX_W) return false;
-    if (p.hash_canonical && !p.strand_tiebreak) return false;  // rare combo -> generic kernel
     const char* env_s = getenv("MZ_FAST_S");
     const char* env_bps = getenv("MZ_FAST_BPS");
     const uint32_t bps = env_bps ? (uint32_t)atoi(env_bps) : 4u;  // resident blocks per SM (target)
@@ -583,6 +582,10 @@ inline int launch_fast_w(const mz_params& p, uint32_t grid, const KArgs& a, cuda
     if (p.strand_tiebreak) {
         return sync ? launch_fast_inst<W, true, true, true>(grid, a, st)
                     : launch_fast_inst<W, true, true, false>(grid, a, st);
+    }
+    if (p.hash_canonical) {  // forward builder + canonical hasher (src/minimizers.rs:69-71)
+        return sync ? launch_fast_inst<W, true, false, true>(grid, a, st)
+                    : launch_fast_inst<W, true, false, false>(grid, a, st);
     }
     return sync ? launch_fast_inst<W, false, false, true>(grid, a, st)
                 : launch_fast_inst<W, false, false, false>(grid, a, st);
