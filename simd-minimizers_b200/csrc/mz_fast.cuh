@@ -458,7 +458,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             uint32_t* const opos = a.pos + (gbase + cbase);
             // sweep 1: fetch each entry's position byte from the L2 scratch (independent loads,
             // unrolled so several are in flight) and fold it into the staged descriptor
-#pragma unroll 4
+#pragma unroll 2
             for (uint32_t x = lane; x < nent; x += 32) {
                 const uint32_t dsc = list[x];
                 const uint32_t t2 = dsc >> 16, e = dsc & 0xffffu, b2 = e / SB, bit2 = e - b2 * SB;
@@ -469,7 +469,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             }
             __syncwarp();
             // sweep 2: positions, super-k-mer starts and k-mer values, coalesced stores
-#pragma unroll 2
+#pragma unroll 1
             for (uint32_t x = lane; x < nent; x += 32) {
                 const uint32_t dsc = list[x];
                 const uint32_t t2 = dsc >> 27, jl = dsc & 0xffffu;
