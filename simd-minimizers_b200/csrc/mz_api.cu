@@ -9,6 +9,7 @@
 #include <cstdio>
 #include <cstring>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "mz_fast.cuh"
@@ -59,6 +60,58 @@ struct DevBuf {
     }
 };
 
+// grow-only pinned host buffer (bounce buffer for callers whose memory is pageable)
+struct PinBuf {
+    unsigned char* p = nullptr;
+    size_t cap = 0;  // bytes
+    int reserve(size_t n) {
+        if (n <= cap) return MZ_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 4096;
+        cudaError_t e = cudaHostAlloc((void**)&p, want, cudaHostAllocPortable);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc", __LINE__);
+        cap = want;
+        return MZ_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+// true when `ptr` is ordinary pageable host memory (cudaMemcpyAsync from/to it is staged by the
+// driver at a fraction of the PCIe rate)
+bool is_pageable(const void* ptr) {
+    if (!ptr) return false;
+    cudaPointerAttributes at{};
+    cudaError_t e = cudaPointerGetAttributes(&at, ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return true;
+    }
+    return at.type == cudaMemoryTypeUnregistered;
+}
+
+// memcpy split over a few host threads (a single thread cannot keep up with a Gen5 x16 link)
+void parallel_memcpy(void* dst, const void* src, size_t bytes) {
+    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (bytes < (8u << 20)) nt = 1;
+    if (nt == 1) {
+        memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> th;
+    const size_t per = (bytes / nt + 4095) & ~size_t(4095);
+    for (unsigned i = 0; i < nt; i++) {
+        const size_t b = std::min(bytes, (size_t)i * per), e = std::min(bytes, b + per);
+        if (e > b) th.emplace_back([=] { memcpy((char*)dst + b, (const char*)src + b, e - b); });
+    }
+    for (auto& t : th) t.join();
+}
+
 struct HostScalars {  // pinned
     unsigned long long count;
     uint32_t ticket;
@@ -82,6 +135,7 @@ struct DevState {
     DevBuf<uint32_t> rlen;
     DevBuf<uint32_t> pread, pwin;  // batch pieces of long reads
     HostScalars* hs = nullptr;
+    PinBuf st_in, st_pos, st_sk, st_val;  // pinned bounce buffers (pageable callers)
 };
 
 }  // namespace
@@ -285,9 +339,14 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
     if (env) chunk = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
     const uint64_t nchunks = (nwin + chunk - 1) / chunk;
     struct Job {
-        uint64_t wb, we, cap, byte_lo;
+        uint64_t wb, we, cap, byte_lo, count = 0, out_off = 0;
         size_t nbytes;
+        bool staged = false;
     };
+    // Pageable caller memory goes through pinned bounce buffers + multi-threaded memcpy; pinned
+    // (mz_host_alloc / cudaHostRegister'ed) memory is used directly.
+    const bool page_in = is_pageable(packed);
+    const bool page_out = is_pageable(out->pos) || (p.want_sk && is_pageable(out->sk)) || (vw && is_pageable(out->val));
     std::vector<Job> jobs(nchunks);
     uint64_t total = 0;
     bool too_small = false;
@@ -308,14 +367,31 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         if ((r = d.pos.reserve(j.cap))) return r;
         if (p.want_sk && (r = d.sk.reserve(j.cap))) return r;
         if (vw && (r = d.val.reserve(j.cap * vw))) return r;
+        const uint8_t* src = packed + j.byte_lo;
+        if (page_in) {
+            if ((r = d.st_in.reserve(j.nbytes))) return r;
+            parallel_memcpy(d.st_in.p, src, j.nbytes);
+            src = d.st_in.p;
+        }
         CK(cudaEventRecord(d.ev[0], d.stream));
-        CK(cudaMemcpyAsync(d.in.p, packed + j.byte_lo, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d.in.p, src, j.nbytes, cudaMemcpyHostToDevice, d.stream));
         CK(cudaEventRecord(d.ev[1], d.stream));
         mz::KArgs a{};
         fill_input_args(a, p, d.in.p, bp_offset, j.byte_lo, j.nbytes, nwin);
         a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
         if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
         CK(cudaEventRecord(d.ev[2], d.stream));
+        return MZ_OK;
+    };
+    // pageable outputs: copy a finished chunk from the bounce buffers into the caller's arrays
+    auto finish = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        Job& j = jobs[c];
+        if (!j.staged || !j.count) return MZ_OK;
+        CK(cudaEventSynchronize(d.ev[3]));
+        parallel_memcpy(out->pos + j.out_off, d.st_pos.p, j.count * 4);
+        if (p.want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4);
+        if (vw) parallel_memcpy(out->val + j.out_off * vw, d.st_val.p, j.count * 8 * vw);
         return MZ_OK;
     };
     auto retire = [&](uint64_t c) -> int {
@@ -346,20 +422,44 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
             count = d.hs->count;
         }
         if (total + count > out->capacity) too_small = true;
+        j.count = count;
+        j.out_off = total;
         if (!too_small && count) {
-            CK(cudaMemcpyAsync(out->pos + total, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
-            if (p.want_sk) CK(cudaMemcpyAsync(out->sk + total, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
-            if (vw) CK(cudaMemcpyAsync(out->val + total * vw, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+            uint32_t *hpos = out->pos + total, *hsk = p.want_sk ? out->sk + total : nullptr;
+            uint64_t* hval = vw ? out->val + total * vw : nullptr;
+            if (page_out) {
+                int r;
+                if ((r = d.st_pos.reserve(count * 4))) return r;
+                if (p.want_sk && (r = d.st_sk.reserve(count * 4))) return r;
+                if (vw && (r = d.st_val.reserve(count * 8 * vw))) return r;
+                hpos = reinterpret_cast<uint32_t*>(d.st_pos.p);
+                hsk = reinterpret_cast<uint32_t*>(d.st_sk.p);
+                hval = reinterpret_cast<uint64_t*>(d.st_val.p);
+                j.staged = true;
+            }
+            CK(cudaMemcpyAsync(hpos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (p.want_sk) CK(cudaMemcpyAsync(hsk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (vw) CK(cudaMemcpyAsync(hval, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+            CK(cudaEventRecord(d.ev[3], d.stream));
         }
         total += count;
         return MZ_OK;
     };
-    for (uint64_t c = 0; c < nchunks; c++) {
-        if ((rc = issue(c))) return rc;
-        if (c + 1 >= (uint64_t)kSlots && (rc = retire(c + 1 - kSlots))) return rc;
+    if (!page_out) {
+        for (uint64_t c = 0; c < nchunks; c++) {
+            if ((rc = issue(c))) return rc;
+            if (c + 1 >= (uint64_t)kSlots && (rc = retire(c + 1 - kSlots))) return rc;
+        }
+        for (uint64_t c = nchunks >= (uint64_t)kSlots ? nchunks - (kSlots - 1) : 0; c < nchunks; c++)
+            if ((rc = retire(c))) return rc;
+    } else {
+        // three stages in flight: kernel(c) | D2H(c-1) into the bounce buffers | memcpy(c-2)
+        for (uint64_t c = 0; c < nchunks + 2; c++) {
+            if (c < nchunks && (rc = issue(c))) return rc;
+            if (c >= 1 && c - 1 < nchunks && (rc = retire(c - 1))) return rc;
+            if (c >= 2 && (rc = finish(c - 2))) return rc;
+        }
     }
-    for (uint64_t c = nchunks >= (uint64_t)kSlots ? nchunks - (kSlots - 1) : 0; c < nchunks; c++)
-        if ((rc = retire(c))) return rc;
     for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(ctx->slot(0, sl).stream));
     out->count = total;
     return too_small ? MZ_ERR_CAPACITY : MZ_OK;
@@ -542,6 +642,7 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.scratch.release(), d.rows.release(), d.ascii.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
         d.offs.release(), d.rstart.release(), d.rlen.release(), d.pread.release(), d.pwin.release();
+        d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release();
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
         if (d.hs) cudaFreeHost(d.hs);
