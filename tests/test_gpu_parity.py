@@ -453,3 +453,26 @@ def test_degenerate_and_dense_outputs_at_scale(sm, oracle):
     rnd = oracle.synth_packed(9, n)
     for (k, w, c, mode) in ((5, 1, True, 0), (8, 2, False, 0), (31, 1, True, 1), (9, 3, True, 2)):
         _check_case(sm, oracle, rnd, 0, n, k, w, c, mode)
+
+
+def test_random_differential_fuzz(sm, oracle):
+    """Seeded random (k, w, len, offset, builder, hasher, mode) combinations against the oracle:
+    broad coverage of kernel instances (every w <= 32 hits the W-specialised kernel, larger w the
+    generic one) and of segment / tile / chunk boundaries."""
+    rng = np.random.default_rng(20261017)
+    base = oracle.synth_packed(4242, 70_000)
+    for it in range(4000):
+        k = int(rng.integers(1, 70))
+        w = int(rng.integers(1, 34)) if rng.random() < 0.85 else int(rng.integers(34, 120))
+        mode = int(rng.choice([0, 0, 0, 1, 2]))
+        canonical = bool(rng.integers(0, 2))
+        if canonical and (k + w - 1) % 2 == 0:
+            w += 1
+        if mode == 2 and w % 2 == 0:
+            mode = 1
+        r = rng.random()
+        n = int(rng.integers(0, 300)) if r < 0.3 else (int(rng.integers(300, 12_000)) if r < 0.9 else int(rng.integers(12_000, 60_000)))
+        off = int(rng.integers(0, 16))
+        kind = "nt" if rng.random() < 0.7 else "mul"
+        hash_canon = canonical or (rng.random() < 0.2)
+        _check_case(sm, oracle, base, off, n, k, w, canonical, mode, kind=kind, hash_canon=hash_canon)
