@@ -222,18 +222,21 @@ int set_smem(K kernel, size_t smem) {
 }
 
 int launch_generic(const mz_params& p, const Plan& pl, const mz::KArgs& a, cudaStream_t st) {
-    const bool hc = p.hash_canonical != 0, lr = p.strand_tiebreak != 0;
+    const bool hc = p.hash_canonical != 0, lr = p.strand_tiebreak != 0, gr = a.scratch != nullptr;
     int rc;
+#define MZ_LAUNCH_GENERIC(HC, LR, GR)                                                     \
+    do {                                                                                  \
+        if ((rc = set_smem(mz::mz_generic_kernel<HC, LR, GR>, pl.smem))) return rc;       \
+        mz::mz_generic_kernel<HC, LR, GR><<<pl.grid, pl.NT, pl.smem, st>>>(a);            \
+    } while (0)
     if (hc && lr) {
-        if ((rc = set_smem(mz::mz_generic_kernel<true, true>, pl.smem))) return rc;
-        mz::mz_generic_kernel<true, true><<<pl.grid, pl.NT, pl.smem, st>>>(a);
+        if (gr) MZ_LAUNCH_GENERIC(true, true, true); else MZ_LAUNCH_GENERIC(true, true, false);
     } else if (hc) {
-        if ((rc = set_smem(mz::mz_generic_kernel<true, false>, pl.smem))) return rc;
-        mz::mz_generic_kernel<true, false><<<pl.grid, pl.NT, pl.smem, st>>>(a);
+        if (gr) MZ_LAUNCH_GENERIC(true, false, true); else MZ_LAUNCH_GENERIC(true, false, false);
     } else {
-        if ((rc = set_smem(mz::mz_generic_kernel<false, false>, pl.smem))) return rc;
-        mz::mz_generic_kernel<false, false><<<pl.grid, pl.NT, pl.smem, st>>>(a);
+        if (gr) MZ_LAUNCH_GENERIC(false, false, true); else MZ_LAUNCH_GENERIC(false, false, false);
     }
+#undef MZ_LAUNCH_GENERIC
     CK(cudaGetLastError());
     return MZ_OK;
 }

@@ -12,7 +12,9 @@ namespace mz {
 // Dynamic shared memory layout of the generic kernel (NT = blockDim.x):
 //   uint2 tab[16]; uint32 misc[8]; emit staging (EMIT_SMEM_BYTES);
 //   uint32 flagw[ceil(S/32)][NT]; uint16 rec[S][NT]; ring[W][NT] (uint2 if LR else uint32)
-template <bool HC, bool LR>
+// GRING: the two-stacks ring lives in global memory (very large w) instead of shared memory;
+// a template flag so that the common case compiles to LDS/STS rather than generic LD/ST.
+template <bool HC, bool LR, bool GRING>
 __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t NT = blockDim.x, tid = threadIdx.x;
@@ -24,7 +26,7 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
     uint16_t* rec = reinterpret_cast<uint16_t*>(flagw + (size_t)nfw * NT);
     // ring starts 8-byte aligned: S*NT*2 bytes with NT multiple of 32 is a multiple of 8
     // very large w: the ring does not fit shared memory and lives in a per-block global region
-    unsigned char* ring_raw = a.scratch
+    unsigned char* ring_raw = GRING
         ? reinterpret_cast<unsigned char*>(a.scratch + (size_t)blockIdx.x * a.scratch_words_per_block)
         : reinterpret_cast<unsigned char*>(rec + (size_t)a.S * NT);
     uint2* ring2 = reinterpret_cast<uint2*>(ring_raw);
