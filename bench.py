@@ -73,20 +73,21 @@ def synth_packed_range(seed: int, base_lo: int, base_hi: int):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons while the timed regions run (20 ms period).  Samples
+    carry nvidia-smi's own timestamp; only those inside a marked busy window are used."""
 
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    Q = ("timestamp,index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index: int):
-        self.idx, self.proc, self.lines = gpu_index, None, []
+        self.idx, self.proc, self.lines, self.windows = gpu_index, None, [], []
 
     def start(self):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-i", str(self.idx), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                 "-i", str(self.idx), "-lms", "20"], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -96,31 +97,42 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
+    def mark(self, t0: float, t1: float):
+        """A timed (busy) window in time.time() seconds."""
+        self.windows.append((t0, t1))
+
     def stop(self) -> dict:
+        import datetime
+
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
+            if len(f) < 10:
                 continue
             try:
-                sm.append(float(f[1])), mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                rows.append((ts, float(f[2]), float(f[3]), f[6:10]))
             except ValueError:
                 continue
+        busy = [r for r in rows if any(a - 0.02 <= r[0] <= b + 0.02 for a, b in self.windows)]
+        use = busy or rows
+        reasons = set()
+        for r in use:
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"), f[5:9]):
+                                "sw_power_cap"), r[3]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in use])) if use else None,
+                "sm_max_mhz": max(r[2] for r in use) if use else None, "reasons": sorted(reasons),
+                "samples": len(use), "samples_total": len(rows)}
 
 
 def measured_peak_gbs():
@@ -285,20 +297,22 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi needs ~0.2 s to start: launch it before the warm-up steps and keep it sampling
+    # (every 20 ms) through the device-resident and the end-to-end timed regions
+    sampler = ClockSampler(local_rank)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         count, _, _ = step_device()
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     dev_ms, launches = [], 0
-    t0 = time.perf_counter()
+    t0, w0 = time.perf_counter(), time.time()
     for _ in range(args.steps):
         count, ms, nl = step_device()
         dev_ms.append(ms)
         launches += nl
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3 / args.steps
-    clocks = sampler.stop()
+    sampler.mark(w0, time.time())
     ms_dev = float(np.mean(dev_ms))
 
     # ---- end to end: pinned host in -> pinned host out through mz_run ------------------------
@@ -319,13 +333,16 @@ def main():
         for _ in range(2):
             c2 = step_e2e()
         barrier()
-        t0 = time.perf_counter()
+        t0, w0 = time.perf_counter(), time.time()
         for _ in range(args.steps):
             c2 = step_e2e()
         barrier()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / args.steps
+        sampler.mark(w0, time.time())
         h2d_bytes = (n_local * 2 + 7) // 8
         d2h_bytes = int(c2) * (4 + 4 * cfg["want_sk"] + 8 * vw)
+
+    clocks = sampler.stop()
 
     # ---- reduce over ranks: max time, sum counts ----------------------------------------------
     stats = torch.tensor([ms_dev, wall_ms, e2e_ms or 0.0, float(count), float(launches),
