@@ -166,6 +166,33 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
 int mz_pack_ascii(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out);
 int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out);
 
+/*
+ * Ambiguous bases.  Replaces
+ *   Builder<'h, true, H, (), SYNCMERS>::run_skip_ambiguous_windows(nseq: PackedNSeq, &mut Vec<u32>)
+ *   (src/lib.rs:451-496; stream src/minimizers.rs:169-214; collector SKIP_MAX
+ *   src/collect.rs:213,243 and src/intrinsics/dedup.rs:147-155; syncmers src/syncmers.rs:152).
+ * A PackedNSeq is the packed 2-bit sequence plus one ambiguity bit per base: base i of the
+ * sequence is bit (amb_bit_offset + i) & 7 of byte (amb_bit_offset + i) >> 3 of `ambiguous`
+ * (LSB first; packed-seq 5.0.0's BitSeq is not in the reference tree, the Rust shim passes its
+ * storage and offset).  Every window of l = k+w-1 bases that contains an ambiguous base produces
+ * nothing; all other windows produce exactly what mz_run produces for them, and the first clean
+ * window after an ambiguous stretch always emits (the reference compares it against SKIPPED).
+ * As in the reference: canonical builders only (MZ_ERR_NOT_CANONICAL otherwise), no super-k-mer
+ * output (want_sk must be 0), minimizers and closed/open syncmers, values as for mz_run.
+ * mz_run_device_skip_ambiguous takes device pointers (like mz_run_device).
+ * mz_pack_ascii_n is `PackedNSeqVec::from_ascii`: 2-bit codes as mz_pack_ascii plus the mask,
+ * (n+7)/8 bytes, bit set for every character outside ACGTacgt; mz_run_ascii_skip_ambiguous
+ * builds both on the device and runs the path.
+ */
+int mz_run_skip_ambiguous(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset,
+                          uint64_t n_bp, const uint8_t* ambiguous, uint64_t amb_bit_offset, mz_out* out);
+int mz_run_device_skip_ambiguous(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_packed,
+                                 uint64_t bp_offset, uint64_t n_bp, const void* d_ambiguous,
+                                 uint64_t amb_bit_offset, uint64_t win_begin, uint64_t win_end,
+                                 mz_out* d_out);
+int mz_pack_ascii_n(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out, uint8_t* ambiguous_out);
+int mz_run_ascii_skip_ambiguous(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out);
+
 int mz_last_timing(const mz_ctx* ctx, mz_timing* t);
 
 #ifdef __cplusplus

@@ -27,6 +27,15 @@ struct PackedSeq {
     PackedSeq slice(uint64_t b, uint64_t e) const { return {data, offset + b, e - b}; }
 };
 
+// packed_seq::PackedNSeq: PackedSeq + one ambiguity bit per base (bit (amb_offset+i)&7 of byte
+// (amb_offset+i)>>3 of `ambiguous`).
+struct PackedNSeq {
+    PackedSeq seq;
+    const uint8_t* ambiguous = nullptr;
+    uint64_t amb_offset = 0;
+    PackedNSeq slice(uint64_t b, uint64_t e) const { return {seq.slice(b, e), ambiguous, amb_offset + b}; }
+};
+
 struct Hasher {  // seq-hash NtHasher<RC> / MulHasher<RC>
     enum Kind { Nt, Mul } kind = Nt;
     uint32_t k = 0;
@@ -89,6 +98,28 @@ public:
     }
     // Appends to min_pos (and to the super-k-mer vector), src/lib.rs:80-81.
     Output run(const PackedSeq& seq, std::vector<uint32_t>& min_pos) const {
+        return run_impl(seq, nullptr, 0, min_pos);
+    }
+    // src/lib.rs:451-496: windows holding an ambiguous base produce nothing.  Canonical builders
+    // without super-k-mers only (a type-state restriction in the reference, checked here).
+    Output run_skip_ambiguous_windows(const PackedNSeq& nseq, std::vector<uint32_t>& min_pos) const {
+        if (!canonical_ || sk_) throw std::logic_error("run_skip_ambiguous_windows: canonical builder without super_kmers() only");
+        if (!nseq.ambiguous) throw std::invalid_argument("PackedNSeq without an ambiguity mask");
+        return run_impl(nseq.seq, nseq.ambiguous, nseq.amb_offset, min_pos);
+    }
+    std::vector<uint32_t> run_skip_ambiguous_windows_once(const PackedNSeq& nseq) const {
+        std::vector<uint32_t> v;
+        run_skip_ambiguous_windows(nseq, v);
+        return v;
+    }
+    std::vector<uint32_t> run_once(const PackedSeq& seq) const {
+        std::vector<uint32_t> v;
+        run(seq, v);
+        return v;
+    }
+
+private:
+    Output run_impl(const PackedSeq& seq, const uint8_t* amb, uint64_t amb_off, std::vector<uint32_t>& min_pos) const {
         mz_params p;
         detail::check(mz_params_nthash(&p, k_, w_, syncmer_, canonical_));
         if (has_hasher_) {
@@ -109,7 +140,8 @@ public:
             if (sk_) sk.resize(cap);
             if (p.value_bits) val.resize(cap);
             mz_out out{pos.data(), sk_ ? sk.data() : nullptr, p.value_bits ? val.data() : nullptr, cap, 0};
-            int rc = mz_run(detail::thread_ctx(), &p, seq.data, seq.offset, seq.len, &out);
+            int rc = amb ? mz_run_skip_ambiguous(detail::thread_ctx(), &p, seq.data, seq.offset, seq.len, amb, amb_off, &out)
+                         : mz_run(detail::thread_ctx(), &p, seq.data, seq.offset, seq.len, &out);
             if (rc == MZ_ERR_CAPACITY) {
                 cap = out.count;
                 continue;
@@ -127,13 +159,7 @@ public:
         if (skip && !val.empty()) val.erase(val.begin());
         return Output(len, std::move(val), &min_pos);
     }
-    std::vector<uint32_t> run_once(const PackedSeq& seq) const {
-        std::vector<uint32_t> v;
-        run(seq, v);
-        return v;
-    }
 
-private:
     uint32_t k_, w_;
     bool canonical_;
     uint32_t syncmer_;

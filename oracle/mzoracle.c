@@ -278,6 +278,76 @@ uint64_t mzo_run(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_para
     return m;
 }
 
+/* ---- ambiguous bases (src/lib.rs:451-496, src/minimizers.rs:169-214) ------------------------
+ * PackedNSeq = packed 2-bit codes + one ambiguity bit per base.  A window that contains an
+ * ambiguous base yields SKIPPED (u32::MAX - 1, src/minimizers.rs:18); the collector then drops
+ * every SKIPPED element and every element equal to the element just before it in the stream
+ * (src/intrinsics/dedup.rs:147-155: the comparison is against the immediately preceding stream
+ * element, skipped or not; test vectors src/test.rs:359-399).
+ * PARITY NOTE: the bit layout of packed-seq 5.0.0's BitSeq is not in the reference tree; the
+ * mask here is one bit per base, base i -> bit (i & 7) of byte i >> 3 (LSB first). */
+#define MZO_SKIPPED 0xfffffffeu
+
+static inline uint32_t amb_bit(const uint8_t* amb, uint64_t off, uint64_t i) {
+    uint64_t p = off + i;
+    return (amb[p >> 3] >> (p & 7)) & 1u;
+}
+
+uint64_t mzo_pack_ascii_n(const char* ascii, uint64_t n, uint8_t* packed_out, uint8_t* amb_out) {
+    memset(amb_out, 0, (n + 7) / 8);
+    for (uint64_t i = 0; i < n; i++) {
+        uint8_t u = (uint8_t)ascii[i] & 0xDFu; /* upper case */
+        if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) amb_out[i >> 3] |= (uint8_t)(1u << (i & 7));
+    }
+    return mzo_pack_ascii(ascii, n, packed_out);
+}
+
+uint64_t mzo_collect_dedup_skip_max(const uint32_t* win_pos, uint64_t nwin, uint32_t* pos_out) {
+    uint64_t m = 0;
+    for (uint64_t j = 0; j < nwin; j++) {
+        uint32_t x = win_pos[j];
+        if (x == MZO_SKIPPED) continue;
+        if (j == 0 || x != win_pos[j - 1]) pos_out[m++] = x;
+    }
+    return m;
+}
+
+uint64_t mzo_run_skip_ambiguous(const uint8_t* packed, uint64_t off, uint64_t n, const uint8_t* amb,
+                                uint64_t amb_off, const mzo_params* p, int algo, uint32_t* pos_out) {
+    if (!params_ok(p)) return (uint64_t)-1;
+    if (!p->strand_tiebreak) return (uint64_t)-1; /* Builder<'h, true, ..>: canonical only */
+    if (n >= (1ull << 32)) return (uint64_t)-1;
+    const uint32_t l = p->k + p->w - 1;
+    if (n < l) return 0;
+    uint64_t nwin = n - l + 1;
+    uint32_t* wp = (uint32_t*)malloc(sizeof(uint32_t) * nwin);
+    if (!wp) return (uint64_t)-1;
+    uint64_t got = algo == 0 ? mzo_window_positions_naive(packed, off, n, p, wp)
+                             : mzo_window_positions_stream(packed, off, n, p, wp);
+    uint64_t m = (uint64_t)-1;
+    if (got == nwin) {
+        if (algo == 0) { /* per window, directly */
+            for (uint64_t j = 0; j < nwin; j++)
+                for (uint32_t t = 0; t < l; t++)
+                    if (amb_bit(amb, amb_off, j + t)) {
+                        wp[j] = MZO_SKIPPED;
+                        break;
+                    }
+        } else { /* running count of ambiguous bases inside the window */
+            uint32_t cnt = 0;
+            for (uint64_t i = 0; i < n; i++) {
+                cnt += amb_bit(amb, amb_off, i);
+                if (i >= l) cnt -= amb_bit(amb, amb_off, i - l);
+                if (i + 1 >= l && cnt) wp[i + 1 - l] = MZO_SKIPPED;
+            }
+        }
+        if (p->mode == MZO_MINIMIZER) m = mzo_collect_dedup_skip_max(wp, nwin, pos_out);
+        else m = mzo_collect_syncmers(wp, nwin, p->w, p->mode == MZO_OPEN_SYNCMER, pos_out);
+    }
+    free(wp);
+    return m;
+}
+
 uint64_t mzo_run_range(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_params* p,
                        uint64_t win_begin, uint64_t win_end, uint32_t* pos_out, uint32_t* sk_out,
                        uint64_t cap) {

@@ -86,6 +86,14 @@ uint64_t mzo_collect_syncmers(const uint32_t* win_pos, uint64_t nwin, uint32_t w
 uint64_t mzo_run(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_params* p,
                  int algo, uint32_t* pos_out, uint32_t* sk_out);
 
+/* Ambiguous bases (PackedNSeq; src/lib.rs:451-496): `amb` holds one bit per base (base i ->
+ * bit (amb_off+i)&7 of byte (amb_off+i)>>3).  Windows containing an ambiguous base produce
+ * nothing; canonical builders only.  mzo_pack_ascii_n: everything except ACGTacgt is ambiguous. */
+uint64_t mzo_pack_ascii_n(const char* ascii, uint64_t n, uint8_t* packed_out, uint8_t* amb_out);
+uint64_t mzo_collect_dedup_skip_max(const uint32_t* win_pos, uint64_t nwin, uint32_t* pos_out);
+uint64_t mzo_run_skip_ambiguous(const uint8_t* packed, uint64_t off, uint64_t n, const uint8_t* amb,
+                                uint64_t amb_off, const mzo_params* p, int algo, uint32_t* pos_out);
+
 /* Fused streaming path writing straight into pos/sk (no per-window array);
  * used for the timed CPU baseline.  Handles windows [win_begin, win_end). */
 uint64_t mzo_run_range(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_params* p,

@@ -73,6 +73,13 @@ def lib():
         L.mzo_values_u64.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint64, u64p]
         L.mzo_values_u128.argtypes = [u8p, C.c_uint64, C.c_uint32, C.c_int, u32p, C.c_uint64, u64p]
         L.mzo_synth_packed.argtypes = [C.c_uint64, C.c_uint64, u8p]
+        L.mzo_pack_ascii_n.argtypes = [C.c_char_p, C.c_uint64, u8p, u8p]
+        L.mzo_pack_ascii_n.restype = C.c_uint64
+        L.mzo_collect_dedup_skip_max.argtypes = [u32p, C.c_uint64, u32p]
+        L.mzo_collect_dedup_skip_max.restype = C.c_uint64
+        L.mzo_run_skip_ambiguous.argtypes = [u8p, C.c_uint64, C.c_uint64, u8p, C.c_uint64,
+                                             C.POINTER(Params), C.c_int, u32p]
+        L.mzo_run_skip_ambiguous.restype = C.c_uint64
         L.mzb_run_mt.argtypes = L.mzo_run_mt.argtypes
         L.mzb_run_mt.restype = C.c_uint64
         L.mzb_have_avx2.restype = C.c_int
@@ -229,3 +236,33 @@ def values_u128(packed, off, length, canonical, pos: np.ndarray) -> np.ndarray:
     out = np.zeros((max(len(pos), 1), 2), dtype=np.uint64)
     lib().mzo_values_u128(_ptr(packed), off, length, int(canonical), _ptr(pos), len(pos), _ptr(out))
     return out[:len(pos)]
+
+
+SKIPPED = 0xFFFFFFFE
+
+
+def pack_ascii_n(seq: bytes):
+    """ASCII -> (packed 2-bit codes, ambiguity bit mask); everything but ACGTacgt is ambiguous."""
+    packed = np.zeros((len(seq) + 3) // 4 + 16, dtype=np.uint8)
+    amb = np.zeros((len(seq) + 7) // 8 + 16, dtype=np.uint8)
+    lib().mzo_pack_ascii_n(seq, len(seq), _ptr(packed), _ptr(amb))
+    return packed, amb
+
+
+def collect_dedup_skip_max(win_pos: np.ndarray) -> np.ndarray:
+    win_pos = np.ascontiguousarray(win_pos, dtype=np.uint32)
+    pos = np.zeros(max(len(win_pos), 1), dtype=np.uint32)
+    m = lib().mzo_collect_dedup_skip_max(_ptr(win_pos), len(win_pos), _ptr(pos))
+    return pos[:m].copy()
+
+
+def run_skip_ambiguous(packed, off, n, amb, amb_off, params: Params, algo: str = "stream"):
+    """run_skip_ambiguous_windows (src/lib.rs:451-496): positions only."""
+    l = params.k + params.w - 1
+    nwin = max(0, n - l + 1)
+    pos = np.zeros(max(nwin, 1), dtype=np.uint32)
+    m = lib().mzo_run_skip_ambiguous(_ptr(packed), off, n, _ptr(amb), amb_off, C.byref(params),
+                                     0 if algo == "naive" else 1, _ptr(pos))
+    if m == ERR:
+        raise ValueError("oracle: invalid parameters")
+    return pos[:m].copy()

@@ -93,4 +93,15 @@ extern "C" {
     pub fn mz_run_ascii(ctx: *mut mz_ctx, p: *const mz_params, ascii: *const c_char, n: u64,
                         out: *mut mz_out) -> c_int;
     pub fn mz_last_timing(ctx: *const mz_ctx, t: *mut mz_timing) -> c_int;
+    pub fn mz_run_skip_ambiguous(ctx: *mut mz_ctx, p: *const mz_params, packed: *const u8, bp_offset: u64,
+                                 n_bp: u64, ambiguous: *const u8, amb_bit_offset: u64,
+                                 out: *mut mz_out) -> c_int;
+    pub fn mz_run_device_skip_ambiguous(ctx: *mut mz_ctx, dev_index: c_int, p: *const mz_params,
+                                        d_packed: *const c_void, bp_offset: u64, n_bp: u64,
+                                        d_ambiguous: *const c_void, amb_bit_offset: u64,
+                                        win_begin: u64, win_end: u64, d_out: *mut mz_out) -> c_int;
+    pub fn mz_pack_ascii_n(ctx: *mut mz_ctx, ascii: *const c_char, n: u64, packed_out: *mut u8,
+                           ambiguous_out: *mut u8) -> c_int;
+    pub fn mz_run_ascii_skip_ambiguous(ctx: *mut mz_ctx, p: *const mz_params, ascii: *const c_char,
+                                       n: u64, out: *mut mz_out) -> c_int;
 }

@@ -5,7 +5,7 @@
 //! Bodies call the C ABI; nothing is computed on the CPU.  Not compiled in this repository's
 //! image (no Rust toolchain) -- see INTEGRATION.md.
 use mzb200_sys as sys;
-use seq_hash::packed_seq::{PackedSeq, Seq};
+use seq_hash::packed_seq::{PackedNSeq, PackedSeq, Seq};
 use std::cell::RefCell;
 
 /// Hashers the device path understands: anything that is a per-base table with a fixed rotation.
@@ -95,12 +95,27 @@ impl<'h, const CANONICAL: bool, const SYNCMER: u8> Builder<'h, CANONICAL, (), SY
         Builder { k: self.k, w: self.w, hasher: Some(h), sk_pos: () }
     }
     pub fn run<'o>(&self, seq: PackedSeq<'_>, min_pos: &'o mut Vec<u32>) -> Output<'o, CANONICAL> {
-        let vals = run_impl::<CANONICAL, SYNCMER>(self.k, self.w, self.hasher, seq, min_pos, None);
+        let vals = run_impl::<CANONICAL, SYNCMER>(self.k, self.w, self.hasher, seq, None, min_pos, None);
         Output { min_pos, vals }
     }
     pub fn run_once(&self, seq: PackedSeq<'_>) -> Vec<u32> {
         let mut v = vec![];
         self.run(seq, &mut v);
+        v
+    }
+}
+/// src/lib.rs:451-496: canonical builders without super-k-mers only.
+impl<'h, const SYNCMER: u8> Builder<'h, true, (), SYNCMER> {
+    pub fn run_skip_ambiguous_windows<'o>(&self, nseq: PackedNSeq<'_>, min_pos: &'o mut Vec<u32>) -> Output<'o, true> {
+        // BitSeq storage + bit offset of base 0 (packed-seq 5.0.0; accessor names to be confirmed
+        // against the crate -- it is not vendored in the reference tree)
+        let (amb, amb_off) = nseq.ambiguous.as_bit_bytes();
+        let vals = run_impl::<true, SYNCMER>(self.k, self.w, self.hasher, nseq.seq, Some((amb, amb_off)), min_pos, None);
+        Output { min_pos, vals }
+    }
+    pub fn run_skip_ambiguous_windows_once(&self, nseq: PackedNSeq<'_>) -> Vec<u32> {
+        let mut v = vec![];
+        self.run_skip_ambiguous_windows(nseq, &mut v);
         v
     }
 }
@@ -112,7 +127,7 @@ impl<'h, const CANONICAL: bool> Builder<'h, CANONICAL, (), 0> {
 }
 impl<'h, 'o2, const CANONICAL: bool> Builder<'h, CANONICAL, &'o2 mut Vec<u32>, 0> {
     pub fn run<'o>(self, seq: PackedSeq<'_>, min_pos: &'o mut Vec<u32>) -> Output<'o, CANONICAL> {
-        let vals = run_impl::<CANONICAL, 0>(self.k, self.w, self.hasher, seq, min_pos, Some(self.sk_pos));
+        let vals = run_impl::<CANONICAL, 0>(self.k, self.w, self.hasher, seq, None, min_pos, Some(self.sk_pos));
         Output { min_pos, vals }
     }
 }
@@ -120,7 +135,7 @@ impl<'h, 'o2, const CANONICAL: bool> Builder<'h, CANONICAL, &'o2 mut Vec<u32>, 0
 /// `Builder::run_impl` / `run_with_buf` (src/lib.rs:386-448, 554-576) -> one `mz_run` call.
 fn run_impl<const CANONICAL: bool, const SYNCMER: u8>(
     k: usize, w: usize, hasher: Option<&dyn TableHasher>, seq: PackedSeq<'_>,
-    min_pos: &mut Vec<u32>, mut sk_pos: Option<&mut Vec<u32>>,
+    ambiguous: Option<(&[u8], usize)>, min_pos: &mut Vec<u32>, mut sk_pos: Option<&mut Vec<u32>>,
 ) -> Vec<u64> {
     let mut p = sys::mz_params::default();
     unsafe { sys::mz_params_nthash(&mut p, k as u32, w as u32, SYNCMER as u32, CANONICAL as u32) };
@@ -150,7 +165,13 @@ fn run_impl<const CANONICAL: bool, const SYNCMER: u8>(
             capacity: cap as u64,
             count: 0,
         };
-        let rc = with_ctx(|c| unsafe { sys::mz_run(c, &p, bytes.as_ptr(), offset as u64, n as u64, &mut out) });
+        let rc = with_ctx(|c| unsafe {
+            match ambiguous {
+                None => sys::mz_run(c, &p, bytes.as_ptr(), offset as u64, n as u64, &mut out),
+                Some((amb, amb_off)) => sys::mz_run_skip_ambiguous(
+                    c, &p, bytes.as_ptr(), offset as u64, n as u64, amb.as_ptr(), amb_off as u64, &mut out),
+            }
+        });
         if rc == sys::MZ_ERR_CAPACITY { cap = out.count as usize; continue; }
         assert!(rc == sys::MZ_OK, "mzb200: {}", err(rc));
         let m = out.count as usize;

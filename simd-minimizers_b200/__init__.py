@@ -27,7 +27,7 @@ from . import _ffi
 from ._ffi import MzError, MzOut, MzParams, MzTiming
 
 __all__ = [
-    "PackedSeq", "PackedSeqVec", "AsciiSeq", "NtHasher", "MulHasher", "U32Vec", "Builder", "Output",
+    "PackedSeq", "PackedSeqVec", "AsciiSeq", "BitSeq", "PackedNSeq", "PackedNSeqVec", "NtHasher", "MulHasher", "U32Vec", "Builder", "Output",
     "minimizers", "canonical_minimizers", "closed_syncmers", "canonical_closed_syncmers",
     "open_syncmers", "canonical_open_syncmers", "canonical_syncmers", "minimizer_positions",
     "canonical_minimizer_positions", "Context", "default_context", "MzError",
@@ -140,6 +140,75 @@ class AsciiSeq:
         ctx = ctx or default_context()
         _check(_ffi.lib().mz_pack_ascii(ctx.handle, self.seq, self.len, data.ctypes.data))
         return PackedSeqVec(data, self.len)
+
+
+class BitSeq:
+    """One bit per base (packed_seq::BitSeq): base i -> bit (offset+i)&7 of byte (offset+i)>>3."""
+
+    def __init__(self, data: np.ndarray, offset: int, length: int):
+        assert data.dtype == np.uint8 and data.flags.c_contiguous
+        assert (offset + length + 7) // 8 <= data.size
+        self.data, self.offset, self.len = data, int(offset), int(length)
+
+    def get(self, i: int) -> int:
+        p = self.offset + i
+        return (int(self.data[p >> 3]) >> (p & 7)) & 1
+
+
+class PackedNSeq:
+    """packed_seq::PackedNSeq: 2-bit codes + ambiguity mask (the codes under ambiguous bases are
+    arbitrary and never influence the output)."""
+
+    def __init__(self, seq: PackedSeq, ambiguous: BitSeq):
+        assert seq.len == ambiguous.len
+        self.seq, self.ambiguous, self.len = seq, ambiguous, seq.len
+
+    def __len__(self):
+        return self.len
+
+    def as_slice(self) -> "PackedNSeq":
+        return self
+
+    def slice(self, start: int, end: int) -> "PackedNSeq":
+        assert 0 <= start <= end <= self.len
+        return PackedNSeq(self.seq.slice(start, end),
+                          BitSeq(self.ambiguous.data, self.ambiguous.offset + start, end - start))
+
+
+class PackedNSeqVec:
+    """Owning PackedNSeq.  ``from_ascii`` runs on the device (mz_pack_ascii_n): every character
+    outside ACGTacgt is ambiguous."""
+
+    def __init__(self, seq: PackedSeqVec, amb: np.ndarray):
+        self.seq, self.amb, self.len = seq, amb, seq.len
+
+    @staticmethod
+    def from_ascii(seq: bytes, ctx: "Context | None" = None) -> "PackedNSeqVec":
+        seq = bytes(seq)
+        n = len(seq)
+        data = np.zeros((n + 3) // 4 + _PAD, dtype=np.uint8)
+        amb = np.zeros((n + 7) // 8 + _PAD, dtype=np.uint8)
+        ctx = ctx or default_context()
+        _check(_ffi.lib().mz_pack_ascii_n(ctx.handle, seq, n, data.ctypes.data, amb.ctypes.data))
+        return PackedNSeqVec(PackedSeqVec(data, n), amb)
+
+    @staticmethod
+    def from_parts(seq: PackedSeqVec, amb_bits: np.ndarray) -> "PackedNSeqVec":
+        """amb_bits: one 0/1 entry per base."""
+        assert amb_bits.size == seq.len
+        amb = np.zeros((seq.len + 7) // 8 + _PAD, dtype=np.uint8)
+        pk = np.packbits(amb_bits.astype(np.uint8), bitorder="little")
+        amb[:pk.size] = pk
+        return PackedNSeqVec(seq, amb)
+
+    def __len__(self):
+        return self.len
+
+    def as_slice(self) -> PackedNSeq:
+        return PackedNSeq(self.seq.as_slice(), BitSeq(self.amb, 0, self.len))
+
+    def slice(self, start: int, end: int) -> PackedNSeq:
+        return self.as_slice().slice(start, end)
 
 
 # ------------------------------------------------------------------------------------------
@@ -273,9 +342,11 @@ def _as_vec(v):
 class Output:
     """src/lib.rs:232-237, 579-630.  ``len`` is k for minimizers, k+w-1 for syncmers."""
 
-    def __init__(self, builder: "Builder", seq: PackedSeq, min_pos: U32Vec, start: int, vals64):
+    def __init__(self, builder: "Builder", seq: PackedSeq, min_pos: U32Vec, start: int, vals64,
+                 src=None, skip: bool = False):
         self.len = builder.k if builder.syncmer == 0 else builder.k + builder.w - 1
         self._b, self.seq, self.min_pos, self._start, self._vals64 = builder, seq, min_pos, start, vals64
+        self._src, self._skip = (src if src is not None else seq), skip
 
     def _values(self, bits: int) -> np.ndarray:
         if self.len > bits // 2:
@@ -286,7 +357,7 @@ class Output:
         if self._start != 0:
             raise NotImplementedError("values of positions appended by an earlier run: call "
                                       "U32Vec.clear() between runs")
-        _, _, vals = self._b._execute(self.seq, value_bits=bits)
+        _, _, vals = self._b._execute(self._src, value_bits=bits, skip=self._skip)
         return vals
 
     def values_u64(self):
@@ -339,7 +410,7 @@ class Builder:
         p.value_bits = value_bits
         return p
 
-    def _execute(self, seq, value_bits: int):
+    def _execute(self, seq, value_bits: int, skip: bool = False):
         seq = seq.as_slice()
         p = self._params(value_bits)
         L = _ffi.lib()
@@ -362,7 +433,13 @@ class Builder:
             val = np.empty(max(cap, 1) * max(vw, 1), dtype=np.uint64) if vw else None
             out = MzOut(pos.ctypes.data, sk.ctypes.data if sk is not None else None,
                         val.ctypes.data if val is not None else None, cap, 0)
-            if isinstance(seq, AsciiSeq):
+            if skip and isinstance(seq, AsciiSeq):
+                rc = L.mz_run_ascii_skip_ambiguous(ctx.handle, C.byref(p), seq.seq, n, C.byref(out))
+            elif skip:
+                rc = L.mz_run_skip_ambiguous(ctx.handle, C.byref(p), seq.seq.data.ctypes.data,
+                                             seq.seq.offset, n, seq.ambiguous.data.ctypes.data,
+                                             seq.ambiguous.offset, C.byref(out))
+            elif isinstance(seq, AsciiSeq):
                 rc = L.mz_run_ascii(ctx.handle, C.byref(p), seq.seq, n, C.byref(out))
             else:
                 rc = L.mz_run(ctx.handle, C.byref(p), seq.data.ctypes.data, seq.offset, n, C.byref(out))
@@ -400,6 +477,31 @@ class Builder:
     def run_once(self, seq) -> np.ndarray:
         v = U32Vec()
         self.run(seq, v)
+        return v.array
+
+    def run_skip_ambiguous_windows(self, nseq, min_pos: U32Vec) -> Output:
+        """src/lib.rs:451-496: windows containing an ambiguous base produce nothing.  ``nseq`` is
+        a PackedNSeq(Vec), or an AsciiSeq (packed and masked on the device).  Canonical builders
+        without super-k-mers only, as in the reference."""
+        if not self.canonical or self._sk_pos is not None:
+            raise TypeError("run_skip_ambiguous_windows needs a canonical builder without super_kmers()")
+        if not isinstance(nseq, (PackedNSeq, PackedNSeqVec, AsciiSeq)):
+            raise TypeError("run_skip_ambiguous_windows takes a PackedNSeq")
+        min_pos = _as_vec(min_pos)
+        length = self.k if self.syncmer == 0 else self.k + self.w - 1
+        pos, _, vals = self._execute(nseq, 64 if length <= 32 else 0, skip=True)
+        start = len(min_pos)
+        if self.syncmer == 0 and start and pos.size and int(pos[0]) == min_pos.last():
+            pos = pos[1:]
+            vals = vals[1:] if vals is not None else None
+        min_pos._extend(pos)
+        src = nseq.as_slice()
+        seq = src.seq if isinstance(src, PackedNSeq) else src
+        return Output(self, seq, min_pos, start, vals, src=src, skip=True)
+
+    def run_skip_ambiguous_windows_once(self, nseq) -> np.ndarray:
+        v = U32Vec()
+        self.run_skip_ambiguous_windows(nseq, v)
         return v.array
 
     def run_batch(self, packed: np.ndarray, *, starts=None, lens=None, stride_bytes: int = 0,

@@ -28,6 +28,8 @@ SYMBOLS = [
     "mz_params_mulhash", "mz_params_set_nthash", "mz_params_set_mulhash", "mz_params_validate",
     "mz_ctx_create", "mz_ctx_destroy", "mz_ctx_device_count", "mz_host_alloc", "mz_host_free",
     "mz_run", "mz_run_device", "mz_run_batch", "mz_pack_ascii", "mz_run_ascii", "mz_last_timing",
+    "mz_run_skip_ambiguous", "mz_run_device_skip_ambiguous", "mz_pack_ascii_n",
+    "mz_run_ascii_skip_ambiguous",
 ]
 
 
@@ -93,6 +95,14 @@ def lib():
     L.mz_pack_ascii.argtypes = [vp, C.c_char_p, C.c_uint64, vp]
     L.mz_run_ascii.argtypes = [vp, C.POINTER(MzParams), C.c_char_p, C.c_uint64, C.POINTER(MzOut)]
     L.mz_last_timing.argtypes = [vp, C.POINTER(MzTiming)]
+    L.mz_run_skip_ambiguous.argtypes = [vp, C.POINTER(MzParams), vp, C.c_uint64, C.c_uint64, vp,
+                                        C.c_uint64, C.POINTER(MzOut)]
+    L.mz_run_device_skip_ambiguous.argtypes = [vp, C.c_int, C.POINTER(MzParams), vp, C.c_uint64,
+                                               C.c_uint64, vp, C.c_uint64, C.c_uint64, C.c_uint64,
+                                               C.POINTER(MzOut)]
+    L.mz_pack_ascii_n.argtypes = [vp, C.c_char_p, C.c_uint64, vp, vp]
+    L.mz_run_ascii_skip_ambiguous.argtypes = [vp, C.POINTER(MzParams), C.c_char_p, C.c_uint64,
+                                              C.POINTER(MzOut)]
     _lib = L
     return L
 

@@ -128,6 +128,7 @@ struct DevState {
     DevBuf<uint32_t> rows;               // fast kernel per-block record rows
     DevBuf<uint8_t> in;
     DevBuf<uint8_t> ascii;               // mz_pack_ascii / mz_run_ascii staging
+    DevBuf<uint8_t> amb;                 // ambiguity mask, one bit per base (skip-ambiguous runs)
     DevBuf<uint32_t> pos, sk;
     DevBuf<uint64_t> val;
     DevBuf<uint64_t> offs;  // batch CSR offsets
@@ -135,7 +136,7 @@ struct DevState {
     DevBuf<uint32_t> rlen;
     DevBuf<uint32_t> pread, pwin;  // batch pieces of long reads
     HostScalars* hs = nullptr;
-    PinBuf st_in, st_pos, st_sk, st_val;  // pinned bounce buffers (pageable callers)
+    PinBuf st_in, st_pos, st_sk, st_val, st_amb;  // pinned bounce buffers (pageable callers)
 };
 
 }  // namespace
@@ -328,12 +329,47 @@ void fill_input_args(mz::KArgs& a, const mz_params& p, const uint8_t* d_in, uint
     a.nwin = nwin;
 }
 
+// Ambiguity mask of a skip-ambiguous run: one bit per base, base g -> bit (off + g) of `bits`.
+struct AmbSrc {
+    const uint8_t* bits = nullptr;
+    uint64_t off = 0;
+};
+
+// Byte range of the mask that covers bases [blo, bhi), start aligned down to 4 bytes.
+void amb_range(const AmbSrc& am, uint64_t blo, uint64_t bhi, uint64_t* byte_lo, size_t* nbytes) {
+    *byte_lo = ((am.off + blo) / 8) & ~uint64_t(3);
+    *nbytes = (size_t)((am.off + bhi + 7) / 8 - *byte_lo);
+}
+
+void fill_amb_args(mz::KArgs& a, const AmbSrc& am, const uint8_t* d_amb, uint64_t byte_lo, size_t nbytes) {
+    a.amb = reinterpret_cast<const uint32_t*>(d_amb);
+    a.amb_bitbias = (int64_t)am.off - (int64_t)(8 * byte_lo);
+    a.amb_nwords = (nbytes + 3) / 4;
+}
+
+// H2D of the mask bytes covering bases [blo, bhi) into d.amb (+ kernel arguments).
+int upload_amb(DevState& d, const AmbSrc& am, uint64_t blo, uint64_t bhi, uint64_t* byte_lo, size_t* nbytes) {
+    amb_range(am, blo, bhi, byte_lo, nbytes);
+    int rc;
+    if ((rc = d.amb.reserve(*nbytes + 64))) return rc;
+    const uint8_t* src = am.bits + *byte_lo;
+    if (is_pageable(am.bits) && *nbytes >= (1u << 20)) {
+        if ((rc = d.st_amb.reserve(*nbytes))) return rc;
+        parallel_memcpy(d.st_amb.p, src, *nbytes);
+        src = d.st_amb.p;
+    }
+    // the word holding the last mask bits may extend past the copied bytes: zero it first
+    CK(cudaMemsetAsync(d.amb.p + (*nbytes & ~size_t(3)), 0, 8, d.stream));
+    CK(cudaMemcpyAsync(d.amb.p, src, *nbytes, cudaMemcpyHostToDevice, d.stream));
+    return MZ_OK;
+}
+
 // Single device, large input: windows are cut into chunks that flow through kSlots streams so
 // that the H2D copy of chunk c+2, the kernel of chunk c+1 and the D2H copy of chunk c overlap.
 // Chunks are seams like any other shard (one extra window on the left); outputs land in the
 // caller's arrays in order.
 int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64_t bp_offset,
-                  uint64_t n_bp, mz_out* out) {
+                  uint64_t n_bp, const AmbSrc& am, mz_out* out) {
     const uint32_t l = p.k + p.w - 1;
     const uint64_t nwin = n_bp - l + 1;
     const uint32_t vw = p.value_bits / 64;
@@ -342,8 +378,8 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
     if (env) chunk = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
     const uint64_t nchunks = (nwin + chunk - 1) / chunk;
     struct Job {
-        uint64_t wb, we, cap, byte_lo, count = 0, out_off = 0;
-        size_t nbytes;
+        uint64_t wb, we, cap, byte_lo, count = 0, out_off = 0, abyte_lo = 0;
+        size_t nbytes, anbytes = 0;
         bool staged = false;
     };
     // Pageable caller memory goes through pinned bounce buffers + multi-threaded memcpy; pinned
@@ -378,9 +414,11 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         }
         CK(cudaEventRecord(d.ev[0], d.stream));
         CK(cudaMemcpyAsync(d.in.p, src, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+        if (am.bits && (r = upload_amb(d, am, blo, j.we + l - 1, &j.abyte_lo, &j.anbytes))) return r;
         CK(cudaEventRecord(d.ev[1], d.stream));
         mz::KArgs a{};
         fill_input_args(a, p, d.in.p, bp_offset, j.byte_lo, j.nbytes, nwin);
+        if (am.bits) fill_amb_args(a, am, d.amb.p, j.abyte_lo, j.anbytes);
         a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
         if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
         CK(cudaEventRecord(d.ev[2], d.stream));
@@ -415,6 +453,7 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
             if (vw && (r = d.val.reserve(j.cap * vw))) return r;
             mz::KArgs a{};
             fill_input_args(a, p, d.in.p, bp_offset, j.byte_lo, j.nbytes, nwin);
+            if (am.bits) fill_amb_args(a, am, d.amb.p, j.abyte_lo, j.anbytes);
             a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
             if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
             CK(cudaStreamSynchronize(d.stream));
@@ -488,6 +527,50 @@ __global__ void mz_pack_ascii_kernel(const uint8_t* __restrict__ ascii, uint64_t
         for (uint64_t j = 0; base + j < n; j++) w |= (uint32_t)((ascii[base + j] >> 1) & 3u) << (2 * j);
     }
     out[i] = w;
+}
+
+// Ambiguity mask of ASCII text: bit = 1 for everything except ACGTacgt; one thread per 32 chars.
+__global__ void mz_amb_ascii_kernel(const uint8_t* __restrict__ ascii, uint64_t n,
+                                    uint32_t* __restrict__ out, uint64_t nwords) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= nwords) return;
+    const uint64_t base = i * 32;
+    uint32_t m = 0;
+    if (base + 32 <= n) {
+        const uint4 v0 = *reinterpret_cast<const uint4*>(ascii + base);
+        const uint4 v1 = *reinterpret_cast<const uint4*>(ascii + base + 16);
+        const uint32_t q[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+            const uint32_t u = q[j] & 0xDFDFDFDFu;  // upper case
+            const uint32_t ok = __vcmpeq4(u, 0x41414141u) | __vcmpeq4(u, 0x43434343u) |
+                                __vcmpeq4(u, 0x47474747u) | __vcmpeq4(u, 0x54545454u);
+            // one bit per byte (multiply-shift gathers bits 0, 8, 16, 24)
+            m |= (((~ok & 0x01010101u) * 0x01020408u) >> 24 & 0xfu) << (4 * j);
+        }
+    } else {
+        for (uint64_t j = 0; base + j < n; j++) {
+            const uint8_t u = ascii[base + j] & 0xDFu;
+            if (!(u == 'A' || u == 'C' || u == 'G' || u == 'T')) m |= 1u << j;
+        }
+    }
+    out[i] = m;
+}
+
+// d.ascii (already on the device) -> ambiguity mask words in d.amb
+int amb_on_device(DevState& d, uint64_t n, size_t* nbytes_out, uint32_t* launches) {
+    const uint64_t nwords = (n + 31) / 32;
+    int rc;
+    if ((rc = d.amb.reserve(nwords * 4 + 64))) return rc;
+    if (nwords) {
+        const uint32_t nt = 256;
+        mz_amb_ascii_kernel<<<(unsigned)((nwords + nt - 1) / nt), nt, 0, d.stream>>>(
+            d.ascii.p, n, reinterpret_cast<uint32_t*>(d.amb.p), nwords);
+        CK(cudaGetLastError());
+        if (launches) (*launches)++;
+    }
+    *nbytes_out = (size_t)nwords * 4;
+    return MZ_OK;
 }
 
 // ascii (host) -> d.ascii -> packed words in d.in; returns packed byte count
@@ -645,7 +728,8 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.scratch.release(), d.rows.release(), d.ascii.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
         d.offs.release(), d.rstart.release(), d.rlen.release(), d.pread.release(), d.pwin.release();
-        d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release();
+        d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release(), d.st_amb.release();
+        d.amb.release();
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
         if (d.hs) cudaFreeHost(d.hs);
@@ -673,12 +757,17 @@ int mz_last_timing(const mz_ctx* ctx, mz_timing* t) {
     return MZ_OK;
 }
 
-int mz_run_device(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_packed,
-                  uint64_t bp_offset, uint64_t n_bp, uint64_t win_begin, uint64_t win_end,
-                  mz_out* out) {
+static int run_device_impl(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_packed,
+                           uint64_t bp_offset, uint64_t n_bp, const void* d_amb, uint64_t amb_bit_offset,
+                           bool skip_ambiguous, uint64_t win_begin, uint64_t win_end, mz_out* out) {
     if (!ctx || !p || !out || dev_index < 0 || dev_index >= (int)ctx->devs.size()) return MZ_ERR_BAD_ARG;
     int rc = mz_params_validate(p, n_bp);
     if (rc) return rc;
+    if (skip_ambiguous) {
+        if (!p->strand_tiebreak) return MZ_ERR_NOT_CANONICAL;  // Builder<'h, true, ..> only, src/lib.rs:451
+        if (p->want_sk) return MZ_ERR_BAD_ARG;                 // ... with SuperKmers = ()
+        if (!d_amb && n_bp) return MZ_ERR_BAD_ARG;
+    }
     out->count = 0;
     const uint32_t l = p->k + p->w - 1;
     if (n_bp < l) return MZ_OK;
@@ -698,6 +787,12 @@ int mz_run_device(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_
     a.bitbias = (int64_t)(8 * (addr - aligned) + 2 * bp_offset);
     a.seq_nwords = ((uint64_t)a.bitbias + 2 * n_bp + 31) / 32;
     a.nwin = nwin;
+    if (skip_ambiguous) {
+        const uintptr_t aaddr = reinterpret_cast<uintptr_t>(d_amb), aal = aaddr & ~uintptr_t(3);
+        a.amb = reinterpret_cast<const uint32_t*>(aal);
+        a.amb_bitbias = (int64_t)(8 * (aaddr - aal) + amb_bit_offset);
+        a.amb_nwords = ((uint64_t)a.amb_bitbias + n_bp + 31) / 32;
+    }
     a.pos = out->pos;
     a.sk = out->sk;
     a.val = out->val;
@@ -714,11 +809,31 @@ int mz_run_device(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_
     return d.hs->overflow ? MZ_ERR_CAPACITY : MZ_OK;
 }
 
-int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset,
-           uint64_t n_bp, mz_out* out) {
+int mz_run_device(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_packed,
+                  uint64_t bp_offset, uint64_t n_bp, uint64_t win_begin, uint64_t win_end,
+                  mz_out* out) {
+    return run_device_impl(ctx, dev_index, p, d_packed, bp_offset, n_bp, nullptr, 0, false, win_begin,
+                           win_end, out);
+}
+
+int mz_run_device_skip_ambiguous(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_packed,
+                                 uint64_t bp_offset, uint64_t n_bp, const void* d_ambiguous,
+                                 uint64_t amb_bit_offset, uint64_t win_begin, uint64_t win_end,
+                                 mz_out* out) {
+    return run_device_impl(ctx, dev_index, p, d_packed, bp_offset, n_bp, d_ambiguous, amb_bit_offset,
+                           true, win_begin, win_end, out);
+}
+
+static int run_host_impl(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset,
+                         uint64_t n_bp, const AmbSrc& am, bool skip_ambiguous, mz_out* out) {
     if (!ctx || !p || !out) return MZ_ERR_BAD_ARG;
     int rc = mz_params_validate(p, n_bp);
     if (rc) return rc;
+    if (skip_ambiguous) {
+        if (!p->strand_tiebreak) return MZ_ERR_NOT_CANONICAL;
+        if (p->want_sk) return MZ_ERR_BAD_ARG;
+        if (!am.bits && n_bp) return MZ_ERR_BAD_ARG;
+    }
     out->count = 0;
     const uint32_t l = p->k + p->w - 1;
     if (n_bp < l) return MZ_OK;
@@ -731,13 +846,14 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
     if (const char* e = getenv("MZ_PIPELINE_MIN_WINDOWS")) pipe_min = strtoull(e, nullptr, 10);
     if (ndev == 1 && nwin >= pipe_min && !getenv("MZ_NO_PIPELINE")) {
         const auto t0 = std::chrono::steady_clock::now();
-        rc = run_pipelined(ctx, *p, packed, bp_offset, n_bp, out);
+        rc = run_pipelined(ctx, *p, packed, bp_offset, n_bp, am, out);
         ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return rc;
     }
 
     struct Shard {
-        uint64_t wb, we, cap, count;
+        uint64_t wb, we, cap, count, abyte_lo = 0;
+        size_t anbytes = 0;
     };
     std::vector<Shard> sh(ndev);
     const uint64_t per = (nwin + ndev - 1) / ndev;
@@ -762,6 +878,7 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
         if (vw && (rc = d.val.reserve(s.cap * vw))) return rc;
         CK(cudaEventRecord(d.ev[0], d.stream));
         CK(cudaMemcpyAsync(d.in.p, packed + byte_lo, nbytes, cudaMemcpyHostToDevice, d.stream));
+        if (am.bits && (rc = upload_amb(d, am, blo, bhi, &s.abyte_lo, &s.anbytes))) return rc;
         CK(cudaEventRecord(d.ev[1], d.stream));
         mz::KArgs a{};
         fill_hash_args(a, *p);
@@ -769,6 +886,7 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
         a.bitbias = (int64_t)(2 * bp_offset) - (int64_t)(8 * byte_lo);
         a.seq_nwords = (nbytes + 3) / 4;
         a.nwin = nwin;
+        if (am.bits) fill_amb_args(a, am, d.amb.p, s.abyte_lo, s.anbytes);
         a.pos = d.pos.p;
         a.sk = d.sk.p;
         a.val = d.val.p;
@@ -798,6 +916,7 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
             a.bitbias = (int64_t)(2 * bp_offset) - (int64_t)(8 * byte_lo);
             a.seq_nwords = (byte_hi - byte_lo + 3) / 4;
             a.nwin = nwin;
+            if (am.bits) fill_amb_args(a, am, d.amb.p, s.abyte_lo, s.anbytes);
             a.pos = d.pos.p;
             a.sk = d.sk.p;
             a.val = d.val.p;
@@ -846,24 +965,53 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
     return MZ_OK;
 }
 
-int mz_pack_ascii(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out) {
-    if (!ctx || (n && (!ascii || !packed_out))) return MZ_ERR_BAD_ARG;
+int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset,
+           uint64_t n_bp, mz_out* out) {
+    return run_host_impl(ctx, p, packed, bp_offset, n_bp, AmbSrc{}, false, out);
+}
+
+int mz_run_skip_ambiguous(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset,
+                          uint64_t n_bp, const uint8_t* ambiguous, uint64_t amb_bit_offset, mz_out* out) {
+    AmbSrc am;
+    am.bits = ambiguous;
+    am.off = amb_bit_offset;
+    return run_host_impl(ctx, p, packed, bp_offset, n_bp, am, true, out);
+}
+
+static int pack_ascii_impl(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out,
+                           uint8_t* amb_out, bool want_amb) {
+    if (!ctx || (n && (!ascii || !packed_out || (want_amb && !amb_out)))) return MZ_ERR_BAD_ARG;
     if (n == 0) return MZ_OK;
     DevState& d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
     ctx->timing = mz_timing{};
-    size_t nbytes = 0;
+    size_t nbytes = 0, anbytes = 0;
     int rc = pack_on_device(d, ascii, n, &nbytes, &ctx->timing.kernel_launches);
     if (rc) return rc;
+    if (want_amb && (rc = amb_on_device(d, n, &anbytes, &ctx->timing.kernel_launches))) return rc;
     CK(cudaMemcpyAsync(packed_out, d.in.p, (n + 3) / 4, cudaMemcpyDeviceToHost, d.stream));
+    if (want_amb) CK(cudaMemcpyAsync(amb_out, d.amb.p, (n + 7) / 8, cudaMemcpyDeviceToHost, d.stream));
     CK(cudaStreamSynchronize(d.stream));
     return MZ_OK;
 }
 
-int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out) {
+int mz_pack_ascii(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out) {
+    return pack_ascii_impl(ctx, ascii, n, packed_out, nullptr, false);
+}
+
+int mz_pack_ascii_n(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_out, uint8_t* ambiguous_out) {
+    return pack_ascii_impl(ctx, ascii, n, packed_out, ambiguous_out, true);
+}
+
+static int run_ascii_impl(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n,
+                          bool skip_ambiguous, mz_out* out) {
     if (!ctx || !p || !out) return MZ_ERR_BAD_ARG;
     int rc = mz_params_validate(p, n);
     if (rc) return rc;
+    if (skip_ambiguous) {
+        if (!p->strand_tiebreak) return MZ_ERR_NOT_CANONICAL;
+        if (p->want_sk) return MZ_ERR_BAD_ARG;
+    }
     out->count = 0;
     const uint32_t l = p->k + p->w - 1;
     if (n < l) return MZ_OK;
@@ -873,6 +1021,8 @@ int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n,
     ctx->timing = mz_timing{};
     size_t nbytes = 0;
     if ((rc = pack_on_device(d, ascii, n, &nbytes, &ctx->timing.kernel_launches))) return rc;
+    size_t anbytes = 0;
+    if (skip_ambiguous && (rc = amb_on_device(d, n, &anbytes, &ctx->timing.kernel_launches))) return rc;
     const uint64_t nwin = n - l + 1;
     const uint32_t vw = p->value_bits / 64;
     uint64_t cap = estimate_capacity(*p, nwin);
@@ -882,6 +1032,7 @@ int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n,
         if (vw && (rc = d.val.reserve(cap * vw))) return rc;
         mz::KArgs a{};
         fill_input_args(a, *p, d.in.p, 0, 0, nbytes, nwin);
+        if (skip_ambiguous) fill_amb_args(a, AmbSrc{}, d.amb.p, 0, anbytes);
         a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = cap;
         if ((rc = enqueue_run(d, *p, a, 0, nwin, &ctx->timing.kernel_launches))) return rc;
         CK(cudaStreamSynchronize(d.stream));
@@ -902,6 +1053,14 @@ int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n,
     }
     CK(cudaStreamSynchronize(d.stream));
     return MZ_OK;
+}
+
+int mz_run_ascii(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out) {
+    return run_ascii_impl(ctx, p, ascii, n, false, out);
+}
+
+int mz_run_ascii_skip_ambiguous(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out) {
+    return run_ascii_impl(ctx, p, ascii, n, true, out);
 }
 
 int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t packed_bytes,

@@ -48,6 +48,11 @@ struct KArgs {
     // long reads: a thread handles one PIECE (S windows) of a read; n_reads then counts pieces
     const uint32_t* piece_read;      // read index of every piece (null: piece == read)
     const uint32_t* piece_win0;      // first window of the piece inside its read
+    // ambiguous bases (PackedNSeq, src/lib.rs:451-496): one bit per base, null = none.
+    // Windows containing an ambiguous base produce nothing (single-sequence mode only).
+    const uint32_t* amb;             // bit of global base g = g + amb_bitbias
+    uint64_t amb_nwords;
+    int64_t amb_bitbias;
 };
 
 __device__ __forceinline__ uint32_t rotl32(uint32_t x, uint32_t r) {
@@ -69,6 +74,44 @@ __device__ __forceinline__ uint32_t ld_bits32(const KArgs& a, uint64_t bit) {
     uint32_t sh = (uint32_t)bit & 31u;
     uint32_t lo = ld_word(a, wi), hi = ld_word(a, wi + 1);
     return __funnelshift_r(lo, hi, sh);
+}
+
+// ---- ambiguity mask (one bit per base) -------------------------------------------------------
+__device__ __forceinline__ uint32_t amb_word(const KArgs& a, uint64_t wi) {
+    return wi < a.amb_nwords ? __ldg(a.amb + wi) : 0u;
+}
+// 32 mask bits starting at bit index `bit`
+__device__ __forceinline__ uint32_t amb_bits32(const KArgs& a, uint64_t bit) {
+    const uint64_t wi = bit >> 5;
+    return __funnelshift_r(amb_word(a, wi), amb_word(a, wi + 1), (uint32_t)bit & 31u);
+}
+// any ambiguous base among the n bases starting at mask bit `bit`?
+static __device__ __noinline__ bool amb_any(const KArgs& a, uint64_t bit, uint32_t n) {
+    for (; n >= 32; n -= 32, bit += 32)
+        if (amb_bits32(a, bit)) return true;
+    return n != 0 && (amb_bits32(a, bit) & ((1u << n) - 1u)) != 0;
+}
+// number of unambiguous bases at the end of the n bases starting at mask bit `bit`
+static __device__ __noinline__ uint32_t amb_clean_run(const KArgs& a, uint64_t bit, uint32_t n) {
+    uint32_t run = 0;
+    for (uint32_t i = 0; i < n; i += 32) {
+        const uint32_t m = amb_bits32(a, bit + i), take = n - i < 32u ? n - i : 32u;
+        for (uint32_t t = 0; t < take; t++) run = ((m >> t) & 1u) ? 0u : run + 1u;
+    }
+    return run;
+}
+// One loop iteration of the fast kernel: bit t of .x <=> the l bases ending at mask bit
+// `bit + t` are all unambiguous (t < n <= 32); `run` = clean run ending just before `bit`,
+// .y = the run after the n bases.
+static __device__ __noinline__ uint2 amb_clean_mask(const KArgs& a, uint64_t bit, uint32_t n, uint32_t l,
+                                                    uint32_t run) {
+    const uint32_t m = amb_bits32(a, bit);
+    uint32_t clean = 0;
+    for (uint32_t t = 0; t < n; t++) {
+        run = ((m >> t) & 1u) ? 0u : run + 1u;
+        if (run >= l) clean |= 1u << t;
+    }
+    return make_uint2(clean, run);
 }
 
 // Sequential reader of 2-bit bases from a bit position.

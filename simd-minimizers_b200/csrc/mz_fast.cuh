@@ -102,7 +102,10 @@ __device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
     return J == 0 ? (w & 0xffu) : J == 3 ? (w >> 24) : __byte_perm(w, 0, 0x4440 + J);
 }
 
-template <int W, bool HC, bool LR, bool SYNC>
+// AMB: windows that contain an ambiguous base (a.amb, one bit per base) produce nothing
+// (run_skip_ambiguous_windows, src/lib.rs:451-496); a separate instance so that the plain path
+// carries no extra state.
+template <int W, bool HC, bool LR, bool SYNC, bool AMB = false>
 __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
     constexpr int B = (int)fast_b(W);    // van-Herk blocks per loop iteration
@@ -219,6 +222,15 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             for (int t = 0; t < W; t++) RL[t] = 0xffffffffu, RR[t] = 0u;
             uint32_t prev = 0xffffffffu, prevlow = 0x100u;
             uint32_t* sp = scr;
+            // ambiguity: only threads whose stretch holds an ambiguous base do any work per block
+            bool amb_here = false;
+            uint32_t zrun = 0, pclean = 0;
+            uint64_t ab0 = 0;
+            if (AMB) {
+                ab0 = (uint64_t)((int64_t)sg.pos_base + a.amb_bitbias);
+                amb_here = amb_any(a, ab0, nelem + k - 1);
+                if (amb_here) zrun = amb_clean_run(a, ab0, k - 1);
+            }
 
             for (uint32_t b = 0; b < NB; b++) {
                 const uint32_t eb = b * SB;
@@ -383,6 +395,17 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     }
                 }
                 prevlow = get_byte(accL[(SB - 1) >> 2], (SB - 1) & 3);
+                uint32_t clean = 0xffffffffu;
+                if (AMB && amb_here) {
+                    // window ending at k-mer eb+t = the l bases ending at local base eb+t+k-1.
+                    // A clean window right after an ambiguous one is always emitted: the
+                    // reference compares against SKIPPED there (src/intrinsics/dedup.rs:147-155).
+                    const uint2 cm = amb_clean_mask(a, ab0 + eb + (k - 1), SB, a.l, zrun);
+                    clean = cm.x;
+                    zrun = cm.y;
+                    if (!SYNC) bf |= ~((clean << 1) | pclean);
+                    pclean = (clean >> (SB - 1)) & 1u;
+                }
                 // keep flags of valid windows only: bit t <-> window-end element eb + t
                 // (only the first and last blocks of a segment can hold invalid windows)
                 if (eb < e_lo + 1u || eb + SB > e_hi) {
@@ -393,6 +416,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     if (!SYNC && sg.first_always && e_lo >= eb && e_lo < eb + SB) bf |= 1u << (e_lo - eb);
                     bf &= mhi & ~mlo;
                 }
+                if (AMB) bf &= clean;
                 flp[b * 32] = bf;
 #pragma unroll
                 for (int q = 0; q < WQ; q++) sp[q * 32] = accL[q];
@@ -565,9 +589,9 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     return true;
 }
 
-template <int W, bool HC, bool LR, bool SYNC>
+template <int W, bool HC, bool LR, bool SYNC, bool AMB = false>
 inline int launch_fast_inst(uint32_t grid, const KArgs& a, cudaStream_t st) {
-    auto kern = mz_fast_kernel<W, HC, LR, SYNC>;
+    auto kern = mz_fast_kernel<W, HC, LR, SYNC, AMB>;
     const size_t smem = fast_smem(a.S, W, a.list_cap);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -591,13 +615,36 @@ inline int launch_fast_w(const mz_params& p, uint32_t grid, const KArgs& a, cuda
                 : launch_fast_inst<W, false, false, false>(grid, a, st);
 }
 
+// skip-ambiguous instances: canonical builders only (src/lib.rs:451)
+template <int W>
+inline int launch_fast_amb_w(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
+    if (!p.strand_tiebreak) return MZ_ERR_NOT_CANONICAL;
+    return p.mode != MZ_MODE_MINIMIZER ? launch_fast_inst<W, true, true, true, true>(grid, a, st)
+                                       : launch_fast_inst<W, true, true, false, true>(grid, a, st);
+}
+
 // defined in mz_fast_g{0..3}.cu (W = 1..8, 9..16, 17..24, 25..32)
 int launch_fast_g0(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 int launch_fast_g1(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 int launch_fast_g2(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 int launch_fast_g3(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 
+// defined in mz_fast_a{0..3}.cu
+int launch_fast_a0(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_a1(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_a2(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_a3(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+
 inline int launch_fast(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
+    if (a.amb) {
+        switch ((p.w - 1) / 8) {
+            case 0: return launch_fast_a0(p, grid, a, st);
+            case 1: return launch_fast_a1(p, grid, a, st);
+            case 2: return launch_fast_a2(p, grid, a, st);
+            case 3: return launch_fast_a3(p, grid, a, st);
+            default: return MZ_ERR_UNSUPPORTED;
+        }
+    }
     switch ((p.w - 1) / 8) {
         case 0: return launch_fast_g0(p, grid, a, st);
         case 1: return launch_fast_g1(p, grid, a, st);

@@ -72,7 +72,17 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
         uint32_t prev = 0xffffffffu, flags = 0;
         const uint32_t nsteps = sg.nvalid + sg.has_prev + l - 1;
         const uint32_t mode = a.mode;
+        // ambiguity mask (run_skip_ambiguous_windows): zrun = unambiguous bases ending at base t
+        const bool amb = a.amb != nullptr;
+        const uint64_t ab0 = (uint64_t)((int64_t)sg.pos_base + a.amb_bitbias);
+        uint32_t zrun = 0, amw = 0;
+        bool pclean = false;
         for (uint32_t t = 0; t < nsteps; t++) {
+            if (amb) {
+                if ((t & 31u) == 0) amw = amb_bits32(a, ab0 + t);
+                zrun = (amw & 1u) ? 0u : zrun + 1u;
+                amw >>= 1;
+            }
             uint32_t b_in = in.next(a);
             uint32_t b_out = t >= k ? out.next(a) : 0u;
             uint2 d = tab[b_in | (b_out << 2)];
@@ -136,6 +146,14 @@ __global__ void __launch_bounds__(256) mz_generic_kernel(const KArgs a) {
             if (mode == MODE_MINIMIZER) flag = (jv == 0 && sg.first_always) || sel != prev;
             else if (mode == MODE_CLOSED) flag = sel == jl || sel == jl + w - 1;
             else flag = sel == jl + w / 2;
+            if (amb) {
+                // a window with an ambiguous base emits nothing; the first clean window after
+                // one is compared against SKIPPED in the reference, i.e. always emitted
+                const bool clean = zrun >= l;
+                if (mode == MODE_MINIMIZER) flag = flag || !pclean;
+                flag = flag && clean;
+                pclean = clean;
+            }
             prev = sel;
             if (jv >= 0) {
                 rec[(uint32_t)jv * NT + tid] = (uint16_t)sel;

@@ -34,6 +34,25 @@ int main() {
         try { canonical_minimizer_positions(seq, 4, 3); } catch (const std::invalid_argument&) { threw = true; }
         assert(threw);  // even l, src/canonical.rs:13-16
     }
+    {   // src/lib.rs:451-496 / src/test.rs:429-482: no reported k-mer holds an ambiguous base, and
+        // a sequence without ambiguous bases gives the plain result
+        const char* s = "ACGTGCTCAGAGANTCAGAGGATTACAGATTACANNNNGATTACAGGATCCA";
+        const size_t n = strlen(s);
+        auto d = pack(s);
+        std::vector<uint8_t> amb((n + 7) / 8 + 16, 0), none((n + 7) / 8 + 16, 0);
+        for (size_t i = 0; i < n; i++)
+            if (s[i] == 'N') amb[i >> 3] |= (uint8_t)(1u << (i & 7));
+        PackedNSeq nseq{{d.data(), 0, n}, amb.data(), 0};
+        auto pos = canonical_minimizers(5, 3).run_skip_ambiguous_windows_once(nseq);
+        assert(!pos.empty());
+        for (uint32_t p : pos)
+            for (uint32_t j = 0; j < 5; j++) assert(s[p + j] != 'N');
+        PackedNSeq clean{{d.data(), 0, n}, none.data(), 0};
+        assert(canonical_minimizers(5, 3).run_skip_ambiguous_windows_once(clean) == canonical_minimizer_positions({d.data(), 0, n}, 5, 3));
+        bool threw = false;
+        try { minimizers(5, 3).run_skip_ambiguous_windows_once(nseq); } catch (const std::logic_error&) { threw = true; }
+        assert(threw);
+    }
     printf("cpp mirror ok\n");
     return 0;
 }

@@ -154,3 +154,75 @@ def test_invalid_params(oracle):
         oracle.run(seq, 0, 100, oracle.make_params(4, 3, canonical=True))       # even l
     with pytest.raises(ValueError):
         oracle.run(seq, 0, 100, oracle.make_params(5, 4, canonical=False, mode=oracle.OPEN_SYNCMER))
+
+
+def test_collect_skip_max_vectors(oracle):
+    """src/test.rs:359-399: SKIPPED elements vanish; the comparison is against the stream
+    element just before (each SIMD lane carries the same stream, so lane 0's output is a
+    prefix of the reference's `out`)."""
+    x = oracle.SKIPPED
+    got = oracle.collect_dedup_skip_max(np.array([0, 1, 1, x, 2, 3, x, x, 4], dtype=np.uint32))
+    assert got.tolist() == [0, 1, 2, 3, 4]
+    got = oracle.collect_dedup_skip_max(np.array([1, x, x, x, x, x, x, 2, x, x, x, x], dtype=np.uint32))
+    assert got.tolist() == [1, 2]
+    # without SKIP_MAX the same stream keeps one x per run (first half of the reference test)
+    pos, _ = oracle.collect_dedup(np.array([0, 1, 1, x, 2, 3, x, x, 4], dtype=np.uint32))
+    assert pos.tolist() == [0, 1, x, 2, 3, x, 4]
+
+
+def _random_n_ascii(rng, n, frac, runs):
+    s = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=n)
+    for _ in range(int(n * frac)):
+        s[rng.integers(0, n)] = ord("N")
+    for _ in range(runs):
+        a = int(rng.integers(0, n))
+        s[a:a + int(rng.integers(1, 200))] = ord("N")
+    return s.tobytes()
+
+
+def test_skip_ambiguous_properties(oracle):
+    """src/test.rs:429-482: no SKIPPED in the output and no ambiguous base inside any reported
+    k-mer; plus naive == streaming, and the equivalent 'filter' formulation: an element of the
+    plain run survives iff its run of windows contains a window without ambiguous bases."""
+    rng = np.random.default_rng(5)
+    for it in range(60):
+        n = int(rng.integers(1, 600))
+        ascii_ = _random_n_ascii(rng, n, 0.01 if it % 2 else 0.0, it % 4)
+        packed, amb = oracle.pack_ascii_n(ascii_)
+        ambits = np.unpackbits(amb, bitorder="little")[:n]
+        assert np.array_equal(ambits, np.frombuffer(ascii_, dtype=np.uint8) == ord("N"))
+        k = int(rng.integers(1, 40))
+        w = int(rng.integers(1, 40))
+        if (k + w - 1) % 2 == 0:
+            w += 1
+        for mode in (oracle.MINIMIZER, oracle.CLOSED_SYNCMER, oracle.OPEN_SYNCMER):
+            if mode == oracle.OPEN_SYNCMER and w % 2 == 0:
+                continue
+            pr = oracle.make_params(k, w, canonical=True, mode=mode)
+            a = oracle.run_skip_ambiguous(packed, 0, n, amb, 0, pr, "naive")
+            b = oracle.run_skip_ambiguous(packed, 0, n, amb, 0, pr, "stream")
+            assert np.array_equal(a, b)
+            l = k + w - 1
+            span = k if mode == oracle.MINIMIZER else l
+            for p in a.tolist():
+                assert p != oracle.SKIPPED
+                assert not ambits[p:p + span].any()
+            # filter formulation
+            nwin = max(0, n - l + 1)
+            clean = np.array([not ambits[j:j + l].any() for j in range(nwin)], dtype=bool)
+            if mode == oracle.MINIMIZER:
+                pos, sk = oracle.run(packed, 0, n, pr, "stream", want_sk=True)
+                ends = np.append(sk[1:], nwin)
+                keep = [bool(clean[s:e].any()) for s, e in zip(sk.tolist(), ends.tolist())]
+                assert np.array_equal(pos[np.array(keep, dtype=bool)] if len(pos) else pos, a)
+            else:
+                pos, _ = oracle.run(packed, 0, n, pr, "stream")
+                assert np.array_equal(pos[clean[pos]] if len(pos) else pos, a)
+    # offsets into both streams
+    ascii_ = _random_n_ascii(rng, 500, 0.01, 2)
+    packed, amb = oracle.pack_ascii_n(ascii_)
+    for off in (1, 2, 3, 5, 9):
+        p2, a2 = oracle.pack_ascii_n(ascii_[off:])
+        pr = oracle.make_params(7, 5, canonical=True)
+        assert np.array_equal(oracle.run_skip_ambiguous(packed, off, 500 - off, amb, off, pr),
+                              oracle.run_skip_ambiguous(p2, 0, 500 - off, a2, 0, pr))
