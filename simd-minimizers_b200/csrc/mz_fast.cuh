@@ -52,8 +52,14 @@ inline size_t fast_smem(uint32_t S, uint32_t W, uint32_t list_cap) {
 inline uint32_t fast_list_cap(uint32_t S, const mz_params& p) {
     const double dens = p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
                       : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
-    const uint32_t want = (uint32_t)(32.0 * S * dens * 1.5) + 64;
-    return std::min<uint32_t>(std::max<uint32_t>((want + 127) / 128 * 128, 256), 4096);
+    static const double slack = getenv("MZ_FAST_LISTF") ? atof(getenv("MZ_FAST_LISTF")) : 1.5;
+    const uint32_t want = (uint32_t)(32.0 * S * dens * slack) + 64;
+    // ... but never more than what keeps the block within 56 KB (4 blocks per SM): dense outputs
+    // (small w) simply take more staging passes per tile
+    const size_t fixed = fast_smem(S, p.w, 0);
+    const uint32_t fit = fixed + 256 * 4 * FAST_WARPS >= 56 * 1024
+                             ? 256u : (uint32_t)((56 * 1024 - fixed) / (4 * FAST_WARPS)) / 128 * 128;
+    return std::max<uint32_t>(std::min<uint32_t>((want + 127) / 128 * 128, std::min<uint32_t>(fit, 4096)), 256);
 }
 
 // Rare path (leftmost != rightmost minimum): strand rule 2*#TG > l on the window's l bases
@@ -572,11 +578,17 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     } else {
         // long segments amortise the (k+w-2)-base warm-up; keep >= ~3 tiles per resident block
         uint64_t want = nwin / (slots * 3 * 32);
-        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 288);
+        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 310);
+        // a thread computes S + w k-mers in whole loop iterations of SB k-mers: pick S so that
+        // the last iteration is full (S = NB*SB - w; 288 -> 304 for w = 19 was worth 3 %)
+        const uint32_t sb = fast_sb(p.w);
+        uint32_t nb = std::max<uint32_t>(1, (s + p.w) / sb);
+        while (nb * sb < p.w + 16) nb++;
+        s = nb * sb - p.w;
     }
-    s = std::max<uint32_t>(16, (s + 15) / 16 * 16);
+    s = std::max<uint32_t>(16, s);
     // flag words live in shared memory (one per W windows): keep ~4 blocks per SM resident
-    while (s > 16 && fast_smem(s, p.w, fast_list_cap(s, p)) > 56 * 1024) s -= 16;
+    while (s > 16 + fast_sb(p.w) && fast_smem(s, p.w, fast_list_cap(s, p)) > 56 * 1024) s -= fast_sb(p.w);
     if ((uint64_t)s + p.w + 2 >= 65535) return false;
     const uint64_t Tt = (uint64_t)32 * s;
     const uint64_t tiles = (nwin + Tt - 1) / Tt;

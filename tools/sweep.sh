@@ -1,3 +1,13 @@
-for s in 224 256 288; do for b in 4 5; do
-echo -n "S=$s BPS=$b: "; MZ_FAST_S=$s MZ_FAST_BPS=$b python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --n-bases 800000000 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"
-done; done
+# S / staging-list sweep of the fast kernel, 3.1 Gbp C2, device-resident
+run() { echo -n "$*: "; env "$@" MZ_FAST_SRAW=1 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; }
+run MZ_FAST_S=304
+run MZ_FAST_S=304 MZ_FAST_LISTF=1.2
+run MZ_FAST_S=304 MZ_FAST_LISTF=1.0
+run MZ_FAST_S=304 MZ_FAST_LISTF=0.7
+run MZ_FAST_S=285
+run MZ_FAST_S=285 MZ_FAST_LISTF=1.1
+run MZ_FAST_S=323
+run MZ_FAST_S=323 MZ_FAST_LISTF=1.1
+run MZ_FAST_S=342 MZ_FAST_LISTF=1.1
+run MZ_FAST_S=266 MZ_FAST_LISTF=1.1
+run MZ_FAST_S=247 MZ_FAST_LISTF=1.1
