@@ -100,6 +100,13 @@ __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
 }
+// Keep a base pointer in registers: without this ptxas re-derives it from kernel parameters in
+// front of every access (several 64-bit adds per load / store in the emission loops).
+template <typename T>
+__device__ __forceinline__ T* pinned(T* p) {
+    asm volatile("" : "+l"(p));
+    return p;
+}
 // J is a compile-time constant after unrolling
 __device__ __forceinline__ uint32_t put_byte(uint32_t acc, uint32_t v, int J) {  // acc.byte[J] = v.byte[0]
     return __byte_perm(acc, v, J == 0 ? 0x3214 : J == 1 ? 0x3240 : J == 2 ? 0x3410 : 0x4210);
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1);
                     if (SB > 16) iw2 = ldw((pin >> 5) + 2), ow2 = ldw((pout >> 5) + 2);
                 }
-                uint32_t preL = 0, preR = 0, bf = 0, tacc = 0, lastR = 0;
+                uint32_t preL = 0, preR = 0, bf = 0, lastR = 0;
                 uint32_t accL[WQ], accR[WQ];
 #pragma unroll
                 for (int q = 0; q < WQ; q++) accL[q] = 0, accR[q] = 0;
@@ -341,10 +348,8 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                         if (two) mR1 = t + 2 < W ? max(preR, s2) : preR;
                         RR[t] = re0;
                         if (two) RR[t + 1] = re1;
-                        tacc |= res0 ^ mR0;  // low half != 0  <=>  leftmost != rightmost
                         accR[(o + t) >> 2] = put_byte(accR[(o + t) >> 2], mR0, (o + t) & 3);
                         if (two) {
-                            tacc |= res1 ^ mR1;
                             accR[(o + t + 1) >> 2] = put_byte(accR[(o + t + 1) >> 2], mR1, (o + t + 1) & 3);
                         }
                         if (o + t == SB - 1) lastR = mR0;
@@ -375,7 +380,14 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     if (LR) RR[q] = max(RR[q], RR[q + 1]);
                 }
                 }  // van-Herk blocks of this iteration
-                if (LR && (tacc & 0xffffu) != 0u) {
+                // leftmost != rightmost somewhere in this iteration?  Compare the position bytes,
+                // four windows per LOP3 (positions inside a window differ by < 256)
+                uint32_t tacc = 0;
+                if (LR) {
+#pragma unroll
+                    for (int q = 0; q < WQ; q++) tacc |= accL[q] ^ accR[q];
+                }
+                if (LR && tacc != 0u) {
                     // cold: some window of this block has leftmost != rightmost.  Apply the strand
                     // rule to those windows and rebuild the block's flags from the position bytes.
                     bf = 0;
@@ -445,7 +457,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
         if (p_valid) {
         const uint32_t tile_e = p_tile, cnt_e = p_cnt, NB_e = p_NB, inc_e = p_inc;
         (void)NB_e;
-        const uint32_t* const scr0 = sc0 + (size_t)(cur ^ 1u) * a.scratch_words_per_block;
+        const uint32_t* const scr0 = pinned(sc0 + (size_t)(cur ^ 1u) * a.scratch_words_per_block);
         const uint32_t* const flr = fl0 + (size_t)(cur ^ 1u) * NBmax * 32 + lane;
         const uint32_t total = __shfl_sync(0xffffffffu, inc_e, 31);
         const uint32_t toff = inc_e - cnt_e;
@@ -461,7 +473,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
         const uint64_t j00 = a.wbeg + (uint64_t)tile_e * 32u * a.S;  // first window of the tile
         const uint32_t hp0 = (a.n_reads == 0 && j00 > 0 && minim) ? 1u : 0u;
         const uint64_t tbit0 = (uint64_t)((int64_t)(2 * (j00 - hp0)) + a.bitbias);  // lane 0's bit0
-        const uint32_t* const twbase = a.seq + (tbit0 >> 5);
+        const uint32_t* const twbase = pinned(a.seq + (tbit0 >> 5));
         const uint32_t tsh = (uint32_t)tbit0 & 31u;
         const uint64_t trem = a.seq_nwords - 1 - (tbit0 >> 5);
         const uint32_t twlim = trem > 0x7ffffff0ull ? 0x7ffffff0u : (uint32_t)trem;
@@ -485,7 +497,9 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
             }
             __syncwarp();
             const uint32_t nent = min(LCAP, total - cbase);
-            uint32_t* const opos = a.pos + (gbase + cbase);
+            uint32_t* const opos = pinned(a.pos + (gbase + cbase));
+            uint32_t* const osk = pinned(a.sk + (a.want_sk ? gbase + cbase : 0ull));
+            unsigned long long* const oval = pinned(reinterpret_cast<unsigned long long*>(a.val) + (a.value_bits == 64 ? gbase + cbase : 0ull));
             if (a.n_reads == 0 && a.value_bits != 0) {
             // Single sequence with values: one software-pipelined pass over the staged entries (entry x is
             // handled by lane x & 31 in all stages, so nothing goes back through shared memory).
@@ -534,7 +548,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                 if (x + 32 < nent) stageB();
                 if (x + 64 < nent) stageA(x + 64);
                 __stcs(opos + x, pos00 - hp0 + rel);  // streaming store: keep the L2 for the scratch rows
-                if (a.want_sk) __stcs(a.sk + (gbase + cbase + x), skv);
+                if (a.want_sk) __stcs(osk + x, skv);
                 if (want64) {
                     const uint32_t sh = (tsh + 2u * rel) & 31u;
                     const uint32_t vlo = __funnelshift_r(c0, c1, sh), vhi = __funnelshift_r(c1, c2, sh);
@@ -545,7 +559,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                         const uint64_t r = (swap_pairs64(__brevll(v)) ^ 0xAAAAAAAAAAAAAAAAull) >> (64 - 2 * len);
                         v = r < v ? r : v;
                     }
-                    __stcs(reinterpret_cast<unsigned long long*>(a.val) + (gbase + cbase + x), (unsigned long long)v);
+                    __stcs(oval + x, (unsigned long long)v);
                 } else if (a.value_bits == 128) {
                     uint64_t lo, hi;
                     kmer_value_u128(a, tbit0 + 2ull * rel, a.val_len, canon_val, lo, hi);
@@ -575,7 +589,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                 if (a.n_reads == 0) {
                     const uint32_t hp = (minim && !(j00 == 0 && t2 == 0)) ? 1u : 0u;
                     __stcs(opos + x, pos00 + t2 * a.S - hp + local);
-                    if (a.want_sk) __stcs(a.sk + (gbase + cbase + x), pos00 + t2 * a.S + (jl - hp));
+                    if (a.want_sk) __stcs(osk + x, pos00 + t2 * a.S + (jl - hp));
                     continue;
                 }
                 const Segment og = make_segment_nt(a, tile_e, t2, 32u);
