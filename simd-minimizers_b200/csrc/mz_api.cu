@@ -137,6 +137,7 @@ struct DevState {
     DevBuf<uint32_t> pread, pwin;  // batch pieces of long reads
     HostScalars* hs = nullptr;
     PinBuf st_in, st_pos, st_sk, st_val, st_amb;  // pinned bounce buffers (pageable callers)
+    PinBuf st_offs;                               // batch: chunk-local CSR offsets on their way out
 };
 
 }  // namespace
@@ -728,7 +729,7 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.scratch.release(), d.rows.release(), d.ascii.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
         d.offs.release(), d.rstart.release(), d.rlen.release(), d.pread.release(), d.pwin.release();
-        d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release(), d.st_amb.release();
+        d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release(), d.st_amb.release(), d.st_offs.release();
         d.amb.release();
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
@@ -1074,12 +1075,14 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     const uint32_t l = p->k + p->w - 1;
     uint32_t max_len = fixed_len_bp;
     uint64_t total_windows = 0;
+    bool monotone = true;  // ragged reads in storage order: the input can be streamed in chunks
     if (read_len_bp) {
         max_len = 0;
         for (uint64_t r = 0; r < n_reads; r++) {
             max_len = std::max(max_len, read_len_bp[r]);
             total_windows += read_len_bp[r] >= l ? read_len_bp[r] - l + 1 : 0;
             if (2 * (read_start_bp[r] + read_len_bp[r]) > 8 * packed_bytes) return MZ_ERR_BAD_ARG;
+            if (r && read_start_bp[r] < read_start_bp[r - 1]) monotone = false;
         }
     } else {
         if (stride_bytes == 0 || (fixed_len_bp + 3) / 4 > stride_bytes) return MZ_ERR_BAD_ARG;
@@ -1095,157 +1098,277 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     if (!packed || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
     const uint32_t S_full = max_len - l + 1;  // windows of the longest read
     const uint32_t vw = p->value_bits / 64;
-    DevState& d = ctx->devs[0];
-    CK(cudaSetDevice(d.device));
+    CK(cudaSetDevice(ctx->devs[0].device));
     ctx->timing = mz_timing{};
+    const auto t_begin = std::chrono::steady_clock::now();
 
     // Geometry.  A thread handles one read when the longest read fits the per-thread record of
     // the chosen kernel; otherwise reads are cut into pieces of S windows (each piece a thread,
     // seam rule as everywhere: one extra window on the left seeds the dedup comparison).
-    Plan pl;
-    mz::FastPlan fp;
     const bool lr = p->strand_tiebreak != 0;
     const bool fast = p->w <= mz::FAST_MAX_W;
-    uint32_t S_cap;
+    uint32_t S_cap, NTg = 128;
     if (fast) {
         S_cap = 288;
         while (S_cap > 16 && mz::fast_smem(S_cap, p->w, mz::fast_list_cap(S_cap, *p)) > 56 * 1024) S_cap -= 16;
     } else {
-        const size_t budget = std::min<size_t>(d.smem_optin, 200 * 1024);
-        pl.NT = 128;
-        while (pl.NT >= 32 && generic_smem(pl.NT, 32, p->w, lr) > budget) pl.NT /= 2;
-        if (pl.NT < 32) {
+        const size_t budget = std::min<size_t>(ctx->devs[0].smem_optin, 200 * 1024);
+        while (NTg >= 32 && generic_smem(NTg, 32, p->w, lr) > budget) NTg /= 2;
+        if (NTg < 32) {
             g_last_error = "mz_run_batch: w too large for the batch kernels";
             return MZ_ERR_UNSUPPORTED;
         }
         S_cap = 512;
-        while (S_cap > 32 && generic_smem(pl.NT, S_cap, p->w, lr) > budget / 2) S_cap -= 32;
+        while (S_cap > 32 && generic_smem(NTg, S_cap, p->w, lr) > budget / 2) S_cap -= 32;
     }
     const uint32_t S = std::min(S_full, S_cap);
     if ((uint64_t)S + p->w + 2 >= 65535) return MZ_ERR_UNSUPPORTED;
-    std::vector<uint32_t> piece_read, piece_win0;
-    uint64_t n_units = n_reads;  // threads needed
-    if (S_full > S_cap) {
-        if (n_reads >= (1ull << 32)) return MZ_ERR_UNSUPPORTED;
-        for (uint64_t r = 0; r < n_reads; r++) {
-            const uint32_t len = read_len_bp ? read_len_bp[r] : fixed_len_bp;
-            const uint32_t nw = len >= l ? len - l + 1 : 0;
-            uint32_t w0 = 0;
-            do {  // every read owns at least one piece (it writes the read's CSR offset)
-                piece_read.push_back((uint32_t)r);
-                piece_win0.push_back(w0);
-                w0 += S;
-            } while (w0 < nw);
-        }
-        n_units = piece_read.size();
-    }
-    if (fast) {
-        const uint64_t tiles = (n_units + 31) / 32;
-        if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
-        fp.S = S;
-        fp.num_tiles = (uint32_t)tiles;
-        fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * 4);
-        fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
-        fp.list_cap = mz::fast_list_cap(S, *p);
-        pl.num_tiles = fp.num_tiles;
-    } else {
-        const uint64_t tiles = (n_units + pl.NT - 1) / pl.NT;
-        if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
-        pl.S = S;
-        pl.smem = generic_smem(pl.NT, S, p->w, lr);
-        pl.num_tiles = (uint32_t)tiles;
-        pl.grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (pl.smem + 1024))));
-    }
+    const bool pieces = S_full > S_cap;
+    if (pieces && n_reads >= (1ull << 32)) return MZ_ERR_UNSUPPORTED;
 
-    uint64_t cap = std::min<uint64_t>(estimate_capacity(*p, total_windows) + n_reads, total_windows);
-    if ((rc = d.in.reserve(packed_bytes + 64))) return rc;
-    if ((rc = d.offs.reserve(n_reads + 1))) return rc;
-    if (read_start_bp) {
-        if ((rc = d.rstart.reserve(n_reads))) return rc;
-        if ((rc = d.rlen.reserve(n_reads))) return rc;
-    }
-    if (!piece_read.empty()) {
-        if ((rc = d.pread.reserve(n_units))) return rc;
-        if ((rc = d.pwin.reserve(n_units))) return rc;
-    }
-    CK(cudaEventRecord(d.ev[0], d.stream));
-    CK(cudaMemcpyAsync(d.in.p, packed, packed_bytes, cudaMemcpyHostToDevice, d.stream));
-    if (!piece_read.empty()) {
-        CK(cudaMemcpyAsync(d.pread.p, piece_read.data(), n_units * 4, cudaMemcpyHostToDevice, d.stream));
-        CK(cudaMemcpyAsync(d.pwin.p, piece_win0.data(), n_units * 4, cudaMemcpyHostToDevice, d.stream));
-    }
-    if (read_start_bp) {
-        CK(cudaMemcpyAsync(d.rstart.p, read_start_bp, n_reads * 8, cudaMemcpyHostToDevice, d.stream));
-        CK(cudaMemcpyAsync(d.rlen.p, read_len_bp, n_reads * 4, cudaMemcpyHostToDevice, d.stream));
-    }
-    CK(cudaEventRecord(d.ev[1], d.stream));
-    for (int attempt = 0; attempt < 2; attempt++) {
-        if ((rc = d.pos.reserve(cap))) return rc;
-        if (p->want_sk && (rc = d.sk.reserve(cap))) return rc;
-        if (vw && (rc = d.val.reserve(cap * vw))) return rc;
-        if ((rc = d.scratch.reserve(2 + (size_t)pl.num_tiles))) return rc;
-        CK(cudaMemsetAsync(d.scratch.p, 0, (2 + (size_t)pl.num_tiles) * sizeof(unsigned long long), d.stream));
+    // Reads are processed in chunks that flow through kSlots streams (H2D of chunk c+1 | kernel
+    // of c | D2H of c-1 | host copy-out of c-2), like the single-sequence path.  Reads that are
+    // not stored in order cannot be streamed: one chunk.
+    uint64_t chunk_reads = std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(1, packed_bytes / n_reads + 1));
+    if (const char* e = getenv("MZ_BATCH_CHUNK_READS")) chunk_reads = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+    chunk_reads = (chunk_reads + 15) & ~uint64_t(15);
+    if (!monotone || chunk_reads > n_reads) chunk_reads = n_reads;
+    const uint64_t nchunks = (n_reads + chunk_reads - 1) / chunk_reads;
+    const bool page_in = is_pageable(packed);
+    const bool page_out = is_pageable(out->pos) || (p->want_sk && is_pageable(out->sk)) || (vw && is_pageable(out->val));
+
+    struct BJob {
+        uint64_t r0 = 0, r1 = 0, byte_lo = 0, windows = 0, n_units = 0, cap = 0, count = 0, out_off = 0;
+        size_t nbytes = 0;
+        uint32_t num_tiles = 0, grid = 0;
+        size_t smem = 0;
+        mz::FastPlan fp;
         mz::KArgs a{};
-        fill_hash_args(a, *p);
-        a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
-        a.bitbias = 0;
-        a.seq_nwords = (packed_bytes + 3) / 4;
-        a.nwin = total_windows;
-        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = cap;
-        a.S = S;
-        a.num_tiles = pl.num_tiles;
+        bool staged = false;
+        std::vector<uint32_t> piece_read, piece_win0;
+    };
+    std::vector<BJob> jobs(nchunks);
+    uint64_t total = 0;
+    bool too_small = false;
+
+    auto launch = [&](DevState& d, BJob& j) -> int {
+        int r;
+        if ((r = d.pos.reserve(j.cap))) return r;
+        if (p->want_sk && (r = d.sk.reserve(j.cap))) return r;
+        if (vw && (r = d.val.reserve(j.cap * vw))) return r;
+        if ((r = d.scratch.reserve(2 + (size_t)j.num_tiles))) return r;
+        CK(cudaMemsetAsync(d.scratch.p, 0, (2 + (size_t)j.num_tiles) * sizeof(unsigned long long), d.stream));
+        mz::KArgs& a = j.a;
+        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
         a.count_out = d.scratch.p;
         a.ticket = reinterpret_cast<uint32_t*>(d.scratch.p + 1);
         a.overflow = a.ticket + 1;
         a.tile_state = d.scratch.p + 2;
-        a.n_reads = n_units;
-        a.piece_read = piece_read.empty() ? nullptr : d.pread.p;
-        a.piece_win0 = piece_read.empty() ? nullptr : d.pwin.p;
+        if (fast) {
+            if ((r = d.rows.reserve(j.fp.scratch_words_per_block * j.fp.grid * mz::FAST_WARPS * 2))) return r;
+            a.scratch = d.rows.p;
+            a.scratch_words_per_block = j.fp.scratch_words_per_block;
+            a.list_cap = j.fp.list_cap;
+            r = mz::launch_fast(*p, j.fp.grid, a, d.stream);
+        } else {
+            Plan pl;
+            pl.NT = NTg, pl.S = S, pl.smem = j.smem, pl.num_tiles = j.num_tiles, pl.grid = j.grid;
+            r = launch_generic(*p, pl, a, d.stream);
+        }
+        if (r) {
+            if (r == MZ_ERR_CUDA && g_last_error.empty()) g_last_error = "kernel launch failed";
+            return r;
+        }
+        ctx->timing.kernel_launches++;
+        CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
+        return MZ_OK;
+    };
+
+    auto issue = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        BJob& j = jobs[c];
+        int r;
+        j.r0 = c * chunk_reads;
+        j.r1 = std::min<uint64_t>(j.r0 + chunk_reads, n_reads);
+        const uint64_t nr = j.r1 - j.r0;
+        // byte range of the chunk's reads (start aligned down to a 32-bit word)
+        uint64_t lo, hi;
+        if (read_start_bp) {
+            if (monotone) {
+                lo = read_start_bp[j.r0] / 4;
+                hi = lo;
+                for (uint64_t r2 = j.r0; r2 < j.r1; r2++) {
+                    hi = std::max<uint64_t>(hi, (read_start_bp[r2] + read_len_bp[r2] + 3) / 4);
+                    j.windows += read_len_bp[r2] >= l ? read_len_bp[r2] - l + 1 : 0;
+                }
+            } else {
+                lo = 0, hi = packed_bytes, j.windows = total_windows;
+            }
+        } else {
+            lo = j.r0 * stride_bytes;
+            hi = (j.r1 - 1) * stride_bytes + (fixed_len_bp + 3) / 4;
+            j.windows = fixed_len_bp >= l ? (uint64_t)(fixed_len_bp - l + 1) * nr : 0;
+        }
+        j.byte_lo = lo & ~uint64_t(3);
+        j.nbytes = (size_t)(hi - j.byte_lo);
+        j.n_units = nr;
+        if (pieces) {
+            for (uint64_t r2 = j.r0; r2 < j.r1; r2++) {
+                const uint32_t len = read_len_bp ? read_len_bp[r2] : fixed_len_bp;
+                const uint32_t nw = len >= l ? len - l + 1 : 0;
+                uint32_t w0 = 0;
+                do {  // every read owns at least one piece (it writes the read's CSR offset)
+                    j.piece_read.push_back((uint32_t)(r2 - j.r0));
+                    j.piece_win0.push_back(w0);
+                    w0 += S;
+                } while (w0 < nw);
+            }
+            j.n_units = j.piece_read.size();
+        }
+        if (fast) {
+            const uint64_t tiles = (j.n_units + 31) / 32;
+            if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
+            j.fp.S = S;
+            j.fp.num_tiles = (uint32_t)tiles;
+            j.fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * 4);
+            j.fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
+            j.fp.list_cap = mz::fast_list_cap(S, *p);
+            j.num_tiles = j.fp.num_tiles;
+        } else {
+            const uint64_t tiles = (j.n_units + NTg - 1) / NTg;
+            if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
+            j.smem = generic_smem(NTg, S, p->w, lr);
+            j.num_tiles = (uint32_t)tiles;
+            j.grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (j.smem + 1024))));
+        }
+        j.cap = std::min<uint64_t>(estimate_capacity(*p, j.windows) + nr, std::max<uint64_t>(j.windows, 1));
+        if ((r = d.in.reserve(j.nbytes + 64))) return r;
+        if ((r = d.offs.reserve(nr + 1))) return r;
+        if (read_start_bp) {
+            if ((r = d.rstart.reserve(nr))) return r;
+            if ((r = d.rlen.reserve(nr))) return r;
+        }
+        if (pieces) {
+            if ((r = d.pread.reserve(j.n_units))) return r;
+            if ((r = d.pwin.reserve(j.n_units))) return r;
+        }
+        const uint8_t* src = packed + j.byte_lo;
+        if (page_in && j.nbytes >= (1u << 20)) {
+            if ((r = d.st_in.reserve(j.nbytes))) return r;
+            parallel_memcpy(d.st_in.p, src, j.nbytes);
+            src = d.st_in.p;
+        }
+        CK(cudaEventRecord(d.ev[0], d.stream));
+        CK(cudaMemcpyAsync(d.in.p, src, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+        if (pieces) {
+            CK(cudaMemcpyAsync(d.pread.p, j.piece_read.data(), j.n_units * 4, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.pwin.p, j.piece_win0.data(), j.n_units * 4, cudaMemcpyHostToDevice, d.stream));
+        }
+        if (read_start_bp) {
+            CK(cudaMemcpyAsync(d.rstart.p, read_start_bp + j.r0, nr * 8, cudaMemcpyHostToDevice, d.stream));
+            CK(cudaMemcpyAsync(d.rlen.p, read_len_bp + j.r0, nr * 4, cudaMemcpyHostToDevice, d.stream));
+        }
+        CK(cudaEventRecord(d.ev[1], d.stream));
+        mz::KArgs& a = j.a;
+        fill_hash_args(a, *p);
+        a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
+        // ragged reads keep their absolute start positions; fixed-stride reads are chunk-local
+        a.bitbias = read_start_bp ? -(int64_t)(8 * j.byte_lo) : (int64_t)(8 * (lo - j.byte_lo));
+        a.seq_nwords = (j.nbytes + 3) / 4;
+        a.nwin = j.windows;
+        a.S = S;
+        a.num_tiles = j.num_tiles;
+        a.n_reads = j.n_units;
+        a.piece_read = pieces ? d.pread.p : nullptr;
+        a.piece_win0 = pieces ? d.pwin.p : nullptr;
         a.read_start_bp = read_start_bp ? d.rstart.p : nullptr;
         a.read_len_bp = read_start_bp ? d.rlen.p : nullptr;
         a.stride_bits = stride_bytes * 8;
         a.fixed_len_bp = fixed_len_bp;
         a.out_offsets = d.offs.p;
-        if (fast) {
-            if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS * 2))) return rc;
-            a.scratch = d.rows.p;
-            a.scratch_words_per_block = fp.scratch_words_per_block;
-            a.list_cap = fp.list_cap;
-            rc = mz::launch_fast(*p, fp.grid, a, d.stream);
-        } else {
-            rc = launch_generic(*p, pl, a, d.stream);
-        }
-        if (rc) {
-            if (rc == MZ_ERR_CUDA && g_last_error.empty()) g_last_error = "kernel launch failed";
-            return rc;
-        }
-        ctx->timing.kernel_launches++;
-        CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
+        if ((r = launch(d, j))) return r;
         CK(cudaEventRecord(d.ev[2], d.stream));
+        return MZ_OK;
+    };
+    // kernel done -> counts known -> D2H of this chunk's outputs and CSR offsets
+    auto retire = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        BJob& j = jobs[c];
+        int r;
         CK(cudaStreamSynchronize(d.stream));
-        if (!d.hs->overflow) break;
-        if (attempt == 1) {
-            g_last_error = "internal: exact-capacity re-run overflowed";
-            return MZ_ERR_CUDA;
+        float h2d = 0, ker = 0;
+        cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
+        cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
+        ctx->timing.h2d_ms += h2d;
+        ctx->timing.kernel_ms += ker;
+        if (d.hs->overflow) {  // capacity estimate too small: redo this chunk with the exact size
+            j.cap = d.hs->count;
+            if ((r = launch(d, j))) return r;
+            CK(cudaStreamSynchronize(d.stream));
+            if (d.hs->overflow) {
+                g_last_error = "internal: exact-capacity re-run overflowed";
+                return MZ_ERR_CUDA;
+            }
         }
-        cap = d.hs->count;
+        const uint64_t count = d.hs->count, nr = j.r1 - j.r0;
+        if (total + count > out->capacity) too_small = true;
+        j.count = count;
+        j.out_off = total;
+        total += count;
+        if (too_small) return MZ_OK;
+        CK(cudaEventRecord(d.ev[2], d.stream));
+        // chunk-local CSR offsets go through pinned memory; the host adds the chunk's base
+        if ((r = d.st_offs.reserve((nr + 1) * 8))) return r;
+        CK(cudaMemcpyAsync(d.st_offs.p, d.offs.p, (nr + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+        if (count) {
+            uint32_t *hpos = out->pos + j.out_off, *hsk = p->want_sk ? out->sk + j.out_off : nullptr;
+            uint64_t* hval = vw ? out->val + j.out_off * vw : nullptr;
+            if (page_out) {
+                if ((r = d.st_pos.reserve(count * 4))) return r;
+                if (p->want_sk && (r = d.st_sk.reserve(count * 4))) return r;
+                if (vw && (r = d.st_val.reserve(count * 8 * vw))) return r;
+                hpos = reinterpret_cast<uint32_t*>(d.st_pos.p);
+                hsk = reinterpret_cast<uint32_t*>(d.st_sk.p);
+                hval = reinterpret_cast<uint64_t*>(d.st_val.p);
+                j.staged = true;
+            }
+            CK(cudaMemcpyAsync(hpos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (p->want_sk) CK(cudaMemcpyAsync(hsk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (vw) CK(cudaMemcpyAsync(hval, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+        }
+        CK(cudaEventRecord(d.ev[3], d.stream));
+        return MZ_OK;
+    };
+    // D2H done -> copy out of the bounce buffers, rebase the CSR offsets
+    auto finish = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        BJob& j = jobs[c];
+        if (too_small) return MZ_OK;
+        CK(cudaEventSynchronize(d.ev[3]));
+        float d2h = 0;
+        cudaEventElapsedTime(&d2h, d.ev[2], d.ev[3]);
+        ctx->timing.d2h_ms += d2h;
+        const uint64_t nr = j.r1 - j.r0;
+        const uint64_t* lo = reinterpret_cast<const uint64_t*>(d.st_offs.p);
+        for (uint64_t i = 1; i <= nr; i++) out_offsets[j.r0 + i] = j.out_off + lo[i];
+        if (j.staged && j.count) {
+            parallel_memcpy(out->pos + j.out_off, d.st_pos.p, j.count * 4);
+            if (p->want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4);
+            if (vw) parallel_memcpy(out->val + j.out_off * vw, d.st_val.p, j.count * 8 * vw);
+        }
+        std::vector<uint32_t>().swap(j.piece_read);
+        std::vector<uint32_t>().swap(j.piece_win0);
+        return MZ_OK;
+    };
+    for (uint64_t c = 0; c < nchunks + 2; c++) {
+        if (c < nchunks && (rc = issue(c))) return rc;
+        if (c >= 1 && c - 1 < nchunks && (rc = retire(c - 1))) return rc;
+        if (c >= 2 && (rc = finish(c - 2))) return rc;
     }
-    const uint64_t count = d.hs->count;
-    out->count = count;
-    if (count > out->capacity) return MZ_ERR_CAPACITY;
-    CK(cudaMemcpyAsync(out_offsets, d.offs.p, (n_reads + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
-    if (count) {
-        CK(cudaMemcpyAsync(out->pos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
-        if (p->want_sk) CK(cudaMemcpyAsync(out->sk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
-        if (vw) CK(cudaMemcpyAsync(out->val, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
-    }
-    CK(cudaEventRecord(d.ev[3], d.stream));
-    CK(cudaStreamSynchronize(d.stream));
-    cudaEventElapsedTime(&ctx->timing.h2d_ms, d.ev[0], d.ev[1]);
-    cudaEventElapsedTime(&ctx->timing.kernel_ms, d.ev[1], d.ev[2]);
-    cudaEventElapsedTime(&ctx->timing.d2h_ms, d.ev[2], d.ev[3]);
-    cudaEventElapsedTime(&ctx->timing.total_ms, d.ev[0], d.ev[3]);
-    return MZ_OK;
+    for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(ctx->slot(0, sl).stream));
+    ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    out->count = total;
+    return too_small ? MZ_ERR_CAPACITY : MZ_OK;
 }
 
 }  // extern "C"

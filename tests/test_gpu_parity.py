@@ -476,3 +476,46 @@ def test_random_differential_fuzz(sm, oracle):
         kind = "nt" if rng.random() < 0.7 else "mul"
         hash_canon = canonical or (rng.random() < 0.2)
         _check_case(sm, oracle, base, off, n, k, w, canonical, mode, kind=kind, hash_canon=hash_canon)
+
+
+@pytest.mark.parametrize("chunk", ["16", "48", "1000"])
+def test_batch_chunk_pipeline_seams(sm, oracle, monkeypatch, chunk):
+    """mz_run_batch streams reads through the device in chunks (MZ_BATCH_CHUNK_READS forces tiny
+    ones): fixed stride, ragged reads in storage order (with long reads cut into pieces), and
+    reads that are NOT in storage order (single-chunk fallback) all give the per-read result,
+    with CSR offsets rebased across chunks."""
+    monkeypatch.setenv("MZ_BATCH_CHUNK_READS", chunk)
+    rng = np.random.default_rng(21)
+    # fixed stride
+    n_reads, read_len, stride = 333, 150, 38
+    packed = oracle.synth_packed(5, n_reads * stride * 4 + 64)
+    starts = np.arange(n_reads, dtype=np.uint64) * (stride * 4)
+    lens = np.full(n_reads, read_len, dtype=np.uint32)
+    sk = sm.U32Vec()
+    offs, pos, sks, vals = sm.canonical_minimizers(21, 11).super_kmers(sk).run_batch(
+        packed, stride_bytes=stride, read_len=read_len, n_reads=n_reads)
+    eo, ep, es, ev = _oracle_batch(oracle, packed, starts, lens, 21, 11, True, 0, True)
+    assert np.array_equal(offs, eo) and np.array_equal(pos, ep) and np.array_equal(sks, es)
+    assert np.array_equal(vals, ev)
+    # ragged, storage order, some long reads
+    n_reads = 260
+    lens = rng.integers(0, 500, n_reads).astype(np.uint32)
+    lens[[7, 100, 259]] = [4000, 9000, 700]
+    starts = np.zeros(n_reads, dtype=np.uint64)
+    cur = 2
+    for i in range(n_reads):
+        starts[i] = cur
+        cur += int(lens[i]) + int(rng.integers(0, 7))
+    packed = oracle.synth_packed(6, cur + 64)
+    for (k, w, c, mode) in ((31, 19, True, 0), (15, 10, False, 1), (9, 40, False, 0)):
+        b = _builder(sm, k, w, c, mode)
+        offs, pos, _, vals = b.run_batch(packed, starts=starts, lens=lens)
+        eo, ep, _, ev = _oracle_batch(oracle, packed, starts, lens, k, w, c, mode, False)
+        assert np.array_equal(offs, eo) and np.array_equal(pos, ep), (k, w, c, mode)
+        if ev is not None:
+            assert np.array_equal(vals, ev)
+    # shuffled order: cannot be streamed
+    perm = rng.permutation(n_reads)
+    offs, pos, _, vals = sm.canonical_minimizers(21, 11).run_batch(packed, starts=starts[perm], lens=lens[perm])
+    eo, ep, _, ev = _oracle_batch(oracle, packed, starts[perm], lens[perm], 21, 11, True, 0, False)
+    assert np.array_equal(offs, eo) and np.array_equal(pos, ep) and np.array_equal(vals, ev)
