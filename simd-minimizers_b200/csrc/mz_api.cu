@@ -1110,7 +1110,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     uint32_t S_cap, NTg = 128;
     if (fast) {
         S_cap = 288;
-        while (S_cap > 16 && mz::fast_smem(S_cap, p->w, mz::fast_list_cap(S_cap, *p)) > 56 * 1024) S_cap -= 16;
+        while (S_cap > 16 && mz::fast_smem(S_cap, p->w, mz::fast_list_cap(S_cap, *p)) > mz::FAST_SMEM_LIMIT) S_cap -= 16;
     } else {
         const size_t budget = std::min<size_t>(ctx->devs[0].smem_optin, 200 * 1024);
         while (NTg >= 32 && generic_smem(NTg, 32, p->w, lr) > budget) NTg /= 2;
@@ -1230,7 +1230,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
             j.fp.S = S;
             j.fp.num_tiles = (uint32_t)tiles;
-            j.fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * 4);
+            j.fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * mz::FAST_BPS);
             j.fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
             j.fp.list_cap = mz::fast_list_cap(S, *p);
             j.num_tiles = j.fp.num_tiles;

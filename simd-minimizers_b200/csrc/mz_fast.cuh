@@ -25,7 +25,15 @@
 namespace mz {
 
 constexpr uint32_t FAST_MAX_W = 32;
-constexpr uint32_t FAST_NT = 128;  // threads per block (compile-time: scratch strides are immediates)
+// One block of 16 autonomous warps per SM.  (Warps never synchronise after start-up, so the block
+// size only decides how many warps share one copy of the hash table in shared memory.)
+constexpr uint32_t FAST_NT = 512;   // threads per block
+constexpr uint32_t FAST_BPS = 1;    // resident blocks per SM
+// The 256-entry delta table is stored FAST_TC times, copy c = lane & 7 interleaved so that entry
+// e of copy c sits at 16-byte slot e*8 + c: the eight lanes of a quarter warp (one LDS.128 pass)
+// always hit eight different bank groups -> no bank conflicts on the random table lookups.
+constexpr uint32_t FAST_TC = 8;
+constexpr size_t FAST_SMEM_LIMIT = 194 * 1024;  // per block (196 KB carve-out): ~60 KB of L1 stay for the input stream
 
 // Per-block scratch in GLOBAL memory (L2-resident: a few hundred KB per resident block, reused
 // for every tile the persistent block processes).  Row r, thread t -> word scratch[r*NT + t]:
@@ -46,7 +54,7 @@ inline size_t fast_scratch_words(uint32_t S, uint32_t W) {
 constexpr uint32_t FAST_WARPS = FAST_NT / 32;
 // shared memory: table | misc | per-warp staging list | per-warp flag words (2 tiles in flight)
 inline size_t fast_smem(uint32_t S, uint32_t W, uint32_t list_cap) {
-    return 256 * 16 + 32 + (size_t)FAST_WARPS * list_cap * 4 + (size_t)FAST_WARPS * 2 * fast_nb(S, W) * 32 * 4;
+    return 256 * FAST_TC * 16 + 32 + (size_t)FAST_WARPS * list_cap * 4 + (size_t)FAST_WARPS * 2 * fast_nb(S, W) * 32 * 4;
 }
 // staging entries per warp: 1.5x the expected emissions of a tile (a second pass handles more)
 inline uint32_t fast_list_cap(uint32_t S, const mz_params& p) {
@@ -54,11 +62,11 @@ inline uint32_t fast_list_cap(uint32_t S, const mz_params& p) {
                       : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
     static const double slack = getenv("MZ_FAST_LISTF") ? atof(getenv("MZ_FAST_LISTF")) : 1.5;
     const uint32_t want = (uint32_t)(32.0 * S * dens * slack) + 64;
-    // ... but never more than what keeps the block within 56 KB (4 blocks per SM): dense outputs
+    // ... but never more than what keeps the block within FAST_SMEM_LIMIT: dense outputs
     // (small w) simply take more staging passes per tile
     const size_t fixed = fast_smem(S, p.w, 0);
-    const uint32_t fit = fixed + 256 * 4 * FAST_WARPS >= 56 * 1024
-                             ? 256u : (uint32_t)((56 * 1024 - fixed) / (4 * FAST_WARPS)) / 128 * 128;
+    const uint32_t fit = fixed + 256 * 4 * FAST_WARPS >= FAST_SMEM_LIMIT
+                             ? 256u : (uint32_t)((FAST_SMEM_LIMIT - fixed) / (4 * FAST_WARPS)) / 128 * 128;
     return std::max<uint32_t>(std::min<uint32_t>((want + 127) / 128 * 128, std::min<uint32_t>(fit, 4096)), 256);
 }
 
@@ -119,7 +127,7 @@ __device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
 // (run_skip_ambiguous_windows, src/lib.rs:451-496); a separate instance so that the plain path
 // carries no extra state.
 template <int W, bool HC, bool LR, bool SYNC, bool AMB = false>
-__global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
+__global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
     constexpr int B = (int)fast_b(W);    // van-Herk blocks per loop iteration
     constexpr int SB = B * W;            // k-mers per loop iteration (<= 32)
@@ -128,7 +136,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint4* T = reinterpret_cast<uint4*>(smem_raw);
-    uint32_t* misc = reinterpret_cast<uint32_t*>(T + 256);
+    uint32_t* misc = reinterpret_cast<uint32_t*>(T + 256 * FAST_TC);
     const uint32_t LCAP = a.list_cap;
     uint32_t* const list = misc + 8 + warp * LCAP;  // this warp's staging list
     const uint32_t NBmax = fast_nb(a.S, W);
@@ -139,13 +147,14 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
 
     const uint32_t k = a.k, R = a.rot & 31u, R2 = (2u * R) & 31u;
     // ---- table: index byte = in0 | in1<<2 | out0<<4 | out1<<6 (two consecutive bases) --------
-    for (uint32_t idx = tid; idx < 256; idx += NT) {
+    for (uint32_t slot = tid; slot < 256 * FAST_TC; slot += NT) {
+        const uint32_t idx = slot / FAST_TC;  // slot = entry * FAST_TC + copy
         const uint32_t in0 = idx & 3u, in1 = (idx >> 2) & 3u, out0 = (idx >> 4) & 3u, out1 = idx >> 6;
         const uint32_t rk = (R * k) & 31u, rk1 = (R * (k - 1)) & 31u;
         const uint32_t f0 = a.f[in0] ^ rotl32(a.f[out0], rk), f1 = a.f[in1] ^ rotl32(a.f[out1], rk);
         const uint32_t c0 = rotl32(a.c[in0], rk1) ^ rotr32(a.c[out0], R);
         const uint32_t c1 = rotl32(a.c[in1], rk1) ^ rotr32(a.c[out1], R);
-        T[idx] = make_uint4(f0, rotl32(f0, R) ^ f1, c0, rotr32(c0, R) ^ c1);
+        T[slot] = make_uint4(f0, rotl32(f0, R) ^ f1, c0, rotr32(c0, R) ^ c1);
     }
     if (tid == 0) {
         uint32_t fa = 0, ca = 0;  // hash state of the virtual all-'A' k-mer before every segment
@@ -156,7 +165,8 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
         misc[1] = fa;
         misc[2] = ca;
     }
-    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T);
+    const uint32_t tcopy = lane & (FAST_TC - 1u);
+    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T) + tcopy * 16u;  // this lane's copy
     uint32_t one;
     asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque constant 1 for imad()
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
@@ -205,12 +215,12 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     rem -= take;
                     pp += 32u;
                     for (; take >= 2; take -= 2, x >>= 4) {
-                        const uint4 e = T[x & 15u];
+                        const uint4 e = T[(x & 15u) * FAST_TC + tcopy];
                         fw = rotl32(fw, R2) ^ e.y;
                         if (HC) rc = rotr32(rc, R2) ^ e.w;
                     }
                     if (take) {
-                        const uint4 e = T[x & 3u];
+                        const uint4 e = T[(x & 3u) * FAST_TC + tcopy];
                         fw = rotl32(fw, R) ^ e.x;
                         if (HC) rc = rotr32(rc, R) ^ e.z;
                     }
@@ -291,7 +301,7 @@ __global__ void __launch_bounds__(FAST_NT, 4) mz_fast_kernel(const KArgs a) {
                     const bool two = t + 1 < W;
                     const uint32_t word = N[(t >> 4) * 2 + ((t >> 1) & 1)];
                     const uint32_t idx = get_byte(word, (t & 15) >> 2);
-                    const uint32_t addr = idx * 16u + tb;
+                    const uint32_t addr = idx * (16u * FAST_TC) + tb;
                     uint32_t h0, h1 = 0;
                     if (HC) {
                         const uint4 e = lds128(addr);
@@ -626,7 +636,7 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     if (p.w > FAST_MAX_W) return false;
     const char* env_s = getenv("MZ_FAST_S");
     const char* env_bps = getenv("MZ_FAST_BPS");
-    const uint32_t bps = env_bps ? (uint32_t)atoi(env_bps) : 4u;  // resident blocks per SM (target)
+    const uint32_t bps = env_bps ? (uint32_t)atoi(env_bps) : FAST_BPS;  // resident blocks per SM
     const uint64_t slots = (uint64_t)sm_count * bps * FAST_WARPS;  // resident warps
     uint32_t s;
     if (env_s) {
@@ -641,10 +651,18 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
         uint32_t nb = std::max<uint32_t>(1, (s + p.w) / sb);
         while (nb * sb < p.w + 16) nb++;
         s = nb * sb - p.w;
+        // dense outputs: shorten the segments until a tile's expected entries fit one staging
+        // pass (a second pass costs more than the longer halo), but keep S >= 160
+        const double dens = p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
+                          : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
+        while (nb > 1 && (nb - 1) * sb >= p.w + 160 && 32.0 * s * dens * 1.15 > fast_list_cap(s, p)) {
+            nb--;
+            s = nb * sb - p.w;
+        }
     }
     s = std::max<uint32_t>(16, s);
     // flag words live in shared memory (one per W windows): keep ~4 blocks per SM resident
-    while (s > 16 + fast_sb(p.w) && fast_smem(s, p.w, fast_list_cap(s, p)) > 56 * 1024) s -= fast_sb(p.w);
+    while (s > 16 + fast_sb(p.w) && fast_smem(s, p.w, fast_list_cap(s, p)) > FAST_SMEM_LIMIT) s -= fast_sb(p.w);
     if ((uint64_t)s + p.w + 2 >= 65535 || fast_nb(s, p.w) >= 2048) return false;  // descriptor: 11-bit iteration
     const uint64_t Tt = (uint64_t)32 * s;
     const uint64_t tiles = (nwin + Tt - 1) / Tt;
