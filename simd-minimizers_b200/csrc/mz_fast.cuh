@@ -147,14 +147,18 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
 
     const uint32_t k = a.k, R = a.rot & 31u, R2 = (2u * R) & 31u;
     // ---- table: index byte = in0 | in1<<2 | out0<<4 | out1<<6 (two consecutive bases) --------
-    for (uint32_t slot = tid; slot < 256 * FAST_TC; slot += NT) {
-        const uint32_t idx = slot / FAST_TC;  // slot = entry * FAST_TC + copy
+    // (forward hash: 8-byte entries read with LDS.64, one pass per half warp -> 16 copies)
+    constexpr uint32_t TCOPIES = HC ? FAST_TC : 2 * FAST_TC;
+    uint2* const T2 = reinterpret_cast<uint2*>(T);
+    for (uint32_t slot = tid; slot < 256 * TCOPIES; slot += NT) {
+        const uint32_t idx = slot / TCOPIES;  // slot = entry * TCOPIES + copy
         const uint32_t in0 = idx & 3u, in1 = (idx >> 2) & 3u, out0 = (idx >> 4) & 3u, out1 = idx >> 6;
         const uint32_t rk = (R * k) & 31u, rk1 = (R * (k - 1)) & 31u;
         const uint32_t f0 = a.f[in0] ^ rotl32(a.f[out0], rk), f1 = a.f[in1] ^ rotl32(a.f[out1], rk);
         const uint32_t c0 = rotl32(a.c[in0], rk1) ^ rotr32(a.c[out0], R);
         const uint32_t c1 = rotl32(a.c[in1], rk1) ^ rotr32(a.c[out1], R);
-        T[slot] = make_uint4(f0, rotl32(f0, R) ^ f1, c0, rotr32(c0, R) ^ c1);
+        if (HC) T[slot] = make_uint4(f0, rotl32(f0, R) ^ f1, c0, rotr32(c0, R) ^ c1);
+        else T2[slot] = make_uint2(f0, rotl32(f0, R) ^ f1);
     }
     if (tid == 0) {
         uint32_t fa = 0, ca = 0;  // hash state of the virtual all-'A' k-mer before every segment
@@ -165,8 +169,13 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
         misc[1] = fa;
         misc[2] = ca;
     }
-    const uint32_t tcopy = lane & (FAST_TC - 1u);
-    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T) + tcopy * 16u;  // this lane's copy
+    const uint32_t tcopy = lane & (TCOPIES - 1u);
+    const uint32_t tb = (uint32_t)__cvta_generic_to_shared(T) + tcopy * (HC ? 16u : 8u);  // this lane's copy
+    auto table = [&](uint32_t idx) -> uint4 {  // entry idx of this lane's copy (prologue only)
+        if (HC) return T[idx * TCOPIES + tcopy];
+        const uint2 e = T2[idx * TCOPIES + tcopy];
+        return make_uint4(e.x, e.y, 0u, 0u);
+    };
     uint32_t one;
     asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque constant 1 for imad()
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
@@ -215,12 +224,12 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                     rem -= take;
                     pp += 32u;
                     for (; take >= 2; take -= 2, x >>= 4) {
-                        const uint4 e = T[(x & 15u) * FAST_TC + tcopy];
+                        const uint4 e = table(x & 15u);
                         fw = rotl32(fw, R2) ^ e.y;
                         if (HC) rc = rotr32(rc, R2) ^ e.w;
                     }
                     if (take) {
-                        const uint4 e = T[(x & 3u) * FAST_TC + tcopy];
+                        const uint4 e = table(x & 3u);
                         fw = rotl32(fw, R) ^ e.x;
                         if (HC) rc = rotr32(rc, R) ^ e.z;
                     }
