@@ -217,3 +217,47 @@ def test_skip_ambiguous_large_pipelined_and_device(sm, oracle, monkeypatch):
     # outside the range start 0; seams inside a clean run dedup against the seam window
     assert np.array_equal(got, want)
     assert np.array_equal(np.concatenate(vparts), wantv)
+
+
+def test_in_process_multi_device_shards(sm, oracle):
+    """mz_run / mz_run_skip_ambiguous with a context that spans every visible GPU: windows are cut
+    into contiguous shards (halo k+w-2 bases + one seam window), outputs gathered in order.
+    Needs >= 2 GPUs (`gpurun --gpus 2`); skipped on a single-GPU box."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs at least two GPUs")
+    ctx = sm.Context(list(range(ndev)))
+    assert ctx.device_count() == ndev
+    n = 30_000_001
+    packed = oracle.synth_packed(13, n + 8)
+    rng = np.random.default_rng(4)
+    bits = np.zeros(n + 8, dtype=np.uint8)
+    for _ in range(30):
+        a = int(rng.integers(0, n))
+        bits[a:a + int(rng.integers(1, 200_000))] = 1
+    # ambiguous stretches across every shard boundary
+    per = (n - 49 + 1 + ndev - 1) // ndev
+    for i in range(1, ndev):
+        bits[i * per - 30:i * per + 10] = 1
+    amb = np.zeros((n + 8 + 7) // 8 + 16, dtype=np.uint8)
+    pk = np.packbits(bits, bitorder="little")
+    amb[:pk.size] = pk
+    off = 3
+    for (k, w, mode) in ((31, 19, 0), (21, 11, 1)):
+        pr = oracle.make_params(k, w, canonical=True, mode=mode)
+        b = {0: sm.canonical_minimizers, 1: sm.canonical_closed_syncmers}[mode](k, w).context(ctx)
+        # plain run (+ super-k-mer starts for minimizers)
+        epos, esk = oracle.run(packed, off, n, pr, "stream", want_sk=(mode == 0))
+        pos, sk = sm.U32Vec(), sm.U32Vec()
+        out = (b.super_kmers(sk) if mode == 0 else b).run(sm.PackedSeq(packed, off, n), pos)
+        assert np.array_equal(pos.array, epos)
+        if mode == 0:
+            assert np.array_equal(sk.array, esk)
+            assert np.array_equal(out.values_u64(), oracle.values_u64(packed, off, k, True, epos))
+        # skip-ambiguous
+        want = oracle.run_skip_ambiguous(packed, off, n, amb, off, pr)
+        nseq = sm.PackedNSeq(sm.PackedSeq(packed, off, n), sm.BitSeq(amb, off, n))
+        got = b.run_skip_ambiguous_windows_once(nseq)
+        assert np.array_equal(got, want)
+    ctx.close()
