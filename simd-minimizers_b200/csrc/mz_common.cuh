@@ -35,8 +35,8 @@ struct KArgs {
     unsigned long long* count_out;   // total entries produced by this launch
     uint32_t* overflow;              // set to 1 when cap was too small
     uint32_t num_tiles;
-    uint32_t* scratch;                 // fast kernel: per-block record rows (L2-resident)
-    uint64_t scratch_words_per_block;
+    uint32_t* scratch;                 // fast kernel: per-warp record rows (L2-resident); generic: global ring
+    uint64_t scratch_words_per_block;  // fast kernel: words per WARP and buffer; generic: per block
     uint32_t list_cap;                 // fast kernel: staging entries per warp and pass
     // batch mode (thread per read); reads == 0 -> single sequence
     uint64_t n_reads;

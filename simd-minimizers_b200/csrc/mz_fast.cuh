@@ -12,10 +12,12 @@
 //   * (hash & 0xffff0000) | pos goes through a prefix-min / suffix-min pair whose W-entry suffix
 //     array lives in registers (static indexing); the rightmost minimum uses max on the
 //     complemented key, exactly the reference's packing (src/sliding_min.rs:190-195,336-341);
-//   * leftmost != rightmost is only OR-accumulated per block; the strand rule
+//   * leftmost != rightmost is detected once per iteration from the packed position bytes of
+//     the two chains (one LOP3 per four windows); the strand rule
 //     (src/canonical.rs) runs in a cold fix-up for the few blocks that contain such a window;
 //   * the low byte of the selected position and a flag bit per window go to an L2-resident
-//     global scratch (coalesced rows); mz_emit.cuh turns them into ordered, coalesced output.
+//     global scratch (coalesced rows); the warp then turns them into ordered, coalesced output
+//     (look-back over tile descriptors, staging list, software-pipelined emission pass).
 #pragma once
 #include "../../include/mz_b200.h"
 #include <algorithm>
@@ -670,7 +672,7 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
         }
     }
     s = std::max<uint32_t>(16, s);
-    // flag words live in shared memory (one per W windows): keep ~4 blocks per SM resident
+    // flag words and staging lists live in shared memory: stay within FAST_SMEM_LIMIT
     while (s > 16 + fast_sb(p.w) && fast_smem(s, p.w, fast_list_cap(s, p)) > FAST_SMEM_LIMIT) s -= fast_sb(p.w);
     if ((uint64_t)s + p.w + 2 >= 65535 || fast_nb(s, p.w) >= 2048) return false;  // descriptor: 11-bit iteration
     const uint64_t Tt = (uint64_t)32 * s;
