@@ -189,6 +189,7 @@ int plan_generic(const DevState& d, const mz_params& p, uint64_t nwin, Plan* pl)
     S = round_up(S, 32);
     const uint32_t wring = global_ring ? 0u : p.w;  // ring entries held in shared memory
     while (S > 32 && generic_smem(NT, S, wring, lr) > budget / 2) S -= 32;
+    if (const char* e = getenv("MZ_GENERIC_S")) S = round_up(std::max(32, atoi(e)), 32);
     if (S + p.w + 2 >= 65535) return MZ_ERR_UNSUPPORTED;
     pl->fast = false;
     pl->NT = NT;
@@ -250,13 +251,14 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
     Plan pl;
     mz::FastPlan fp;
     int rc = MZ_OK;
-    if (mz::plan_fast(d.sm_count, p, wend - wbeg, &fp)) {
+    if (mz::plan_fast(d.sm_count, p, wend - wbeg, &fp, /*allow_xw=*/a.amb == nullptr && a.n_reads == 0)) {
         pl.fast = true;
         pl.S = fp.S;
         pl.num_tiles = fp.num_tiles;
-        if ((rc = d.rows.reserve(fp.scratch_words_per_block * fp.grid * mz::FAST_WARPS * 2))) return rc;
+        if ((rc = d.rows.reserve((fp.scratch_words_per_block * 2 + fp.r1_words) * fp.grid * mz::FAST_WARPS))) return rc;
         a.scratch = d.rows.p;
         a.scratch_words_per_block = fp.scratch_words_per_block;
+        a.r1_words_per_warp = fp.r1_words;
         a.list_cap = fp.list_cap;
     } else {
         rc = plan_generic(d, p, wend - wbeg, &pl);

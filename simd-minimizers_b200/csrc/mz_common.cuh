@@ -38,6 +38,7 @@ struct KArgs {
     uint32_t* scratch;                 // fast kernel: per-warp record rows (L2-resident); generic: global ring
     uint64_t scratch_words_per_block;  // fast kernel: words per WARP and buffer; generic: per block
     uint32_t list_cap;                 // fast kernel: staging entries per warp and pass
+    uint64_t r1_words_per_warp;        // fast kernel, w > 32: level-1 result rows per warp (else 0)
     // batch mode (thread per read); reads == 0 -> single sequence
     uint64_t n_reads;
     const uint64_t* read_start_bp;   // may be null -> fixed stride

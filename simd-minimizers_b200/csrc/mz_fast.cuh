@@ -46,12 +46,34 @@ constexpr size_t FAST_SMEM_LIMIT = 194 * 1024;  // per block (196 KB carve-out):
 __host__ __device__ constexpr uint32_t fast_b(uint32_t W) { return W <= 16 ? 32 / W : 1; }
 __host__ __device__ constexpr uint32_t fast_sb(uint32_t W) { return fast_b(W) * W; }
 __host__ __device__ constexpr uint32_t fast_wq(uint32_t W) { return (fast_sb(W) + 3) / 4; }
-__host__ __device__ inline uint32_t fast_nb(uint32_t S, uint32_t W) {
-    return (S + 1 + (W - 1) + fast_sb(W) - 1) / fast_sb(W);  // k-mers = S + has_prev + W - 1
+// Windows longer than FAST_MAX_W (XW instances): the minimum over w k-mers is the minimum over
+// T+1 shifted sub-windows of wt = fast_wt(w) <= 24 k-mers each; the kernel instance is the one of
+// wt.  For w <= FAST_MAX_W, wt = w.
+constexpr uint32_t FAST_XW_MAX_W = 255;  // selected position - window start must fit a byte
+__host__ __device__ inline uint32_t fast_wt(uint32_t w) {
+    if (w <= FAST_MAX_W) return w;
+    const uint32_t parts = (w + 23) / 24;
+    return (w + parts - 1) / parts;
+}
+__host__ __device__ inline uint32_t fast_nb(uint32_t S, uint32_t w) {
+    const uint32_t sb = fast_sb(fast_wt(w));
+    return (S + 1 + (w - 1) + sb - 1) / sb;  // k-mers = S + has_prev + w - 1
 }
 // scratch words per WARP (a warp is an autonomous worker: tile = 32 threads x S windows)
-inline size_t fast_scratch_words(uint32_t S, uint32_t W) {
-    return (size_t)fast_nb(S, W) * fast_wq(W) * 32;
+inline size_t fast_scratch_words(uint32_t S, uint32_t w) {
+    return (size_t)fast_nb(S, w) * fast_wq(fast_wt(w)) * 32;
+}
+// XW instances: words per warp for the ring of level-1 results (one row of 32 lanes per k-mer;
+// leftmost and rightmost sub-window minimum for strand-aware builders)
+__host__ __device__ inline uint32_t fast_ring_rows(uint32_t w) {  // power of two >= (w - wt) + iteration
+    const uint32_t need = (w - fast_wt(w)) + fast_sb(fast_wt(w)) + 4;
+    uint32_t r = 32;
+    while (r < need) r <<= 1;
+    return r;
+}
+inline size_t fast_r1_words(uint32_t S, uint32_t w, bool lr) {
+    (void)S;
+    return w <= FAST_MAX_W ? 0 : (size_t)fast_ring_rows(w) * 32 * (lr ? 2 : 1);
 }
 constexpr uint32_t FAST_WARPS = FAST_NT / 32;
 // shared memory: table | misc | per-warp staging list | per-warp flag words (2 tiles in flight)
@@ -128,9 +150,15 @@ __device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
 // AMB: windows that contain an ambiguous base (a.amb, one bit per base) produce nothing
 // (run_skip_ambiguous_windows, src/lib.rs:451-496); a separate instance so that the plain path
 // carries no extra state.
-template <int W, bool HC, bool LR, bool SYNC, bool AMB = false>
+// XW: a.w > FAST_MAX_W.  The van-Herk machinery computes the minima of sub-windows of W k-mers;
+// they go through a small per-warp ring of rows in the L2 scratch, and the minimum of the real
+// window is the minimum over the T+1 shifted sub-windows that cover it (the current one from
+// registers, the others read back from the ring a group of four k-mers ahead of use).  Everything
+// downstream (flags, position bytes, strand fix-up, emission) sees the real-window result.
+template <int W, bool HC, bool LR, bool SYNC, bool AMB = false, bool XW = false>
 __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
+    static_assert(!(XW && AMB), "no skip-ambiguous instances for long windows");
     constexpr int B = (int)fast_b(W);    // van-Herk blocks per loop iteration
     constexpr int SB = B * W;            // k-mers per loop iteration (<= 32)
     constexpr int WQ = (SB + 3) / 4;     // record words per iteration
@@ -141,11 +169,13 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
     uint32_t* misc = reinterpret_cast<uint32_t*>(T + 256 * FAST_TC);
     const uint32_t LCAP = a.list_cap;
     uint32_t* const list = misc + 8 + warp * LCAP;  // this warp's staging list
-    const uint32_t NBmax = fast_nb(a.S, W);
+    const uint32_t Wr = XW ? a.w : (uint32_t)W;  // real window length
+    const uint32_t NBmax = fast_nb(a.S, Wr);
     // flag words of this warp, two tiles in flight: fl0[buf][b*32 + lane]
     uint32_t* const fl0 = misc + 8 + FAST_WARPS * LCAP + (size_t)warp * 2 * NBmax * 32;
     // this warp's record rows in global scratch (two buffers): row r, lane t -> sc0[buf][r*32 + t]
-    uint32_t* const sc0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * 2 * a.scratch_words_per_block;
+    uint32_t* const sc0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * (2 * a.scratch_words_per_block + a.r1_words_per_warp);
+    uint32_t* const r1 = sc0 + 2 * a.scratch_words_per_block;  // XW: level-1 rows of this warp
 
     const uint32_t k = a.k, R = a.rot & 31u, R2 = (2u * R) & 31u;
     // ---- table: index byte = in0 | in1<<2 | out0<<4 | out1<<6 (two consecutive bases) --------
@@ -181,7 +211,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
     uint32_t one;
     asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque constant 1 for imad()
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
-    const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (W - 1) / 2, so2 = a.mode == MODE_CLOSED ? W - 1 : (W - 1) / 2;
+    const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (Wr - 1) / 2, so2 = a.mode == MODE_CLOSED ? Wr - 1 : (Wr - 1) / 2;
 
     __syncthreads();  // table + misc ready; from here on every warp works on its own
     const bool minim = a.mode == MODE_MINIMIZER;
@@ -202,10 +232,10 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
 
         if (sg.nvalid) {
             uint32_t fw = misc[1], rc = misc[2];
-            const uint32_t nelem = sg.nvalid + sg.has_prev + (W - 1);
+            const uint32_t nelem = sg.nvalid + sg.has_prev + (Wr - 1);
             NB = (nelem + SB - 1) / SB;
             // first/last valid window-end element: e = jl + W - 1, jl in [has_prev, has_prev + nvalid)
-            const uint32_t e_lo = sg.has_prev + (W - 1), e_hi = e_lo + sg.nvalid;
+            const uint32_t e_lo = sg.has_prev + (Wr - 1), e_hi = e_lo + sg.nvalid;
 
             // ---- thread-local view of the packed stream (32-bit word offsets) ----------------
             // Entering bases of block b start at local base k-1+bW; leaving bases at local base
@@ -256,6 +286,11 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
             for (int t = 0; t < W; t++) RL[t] = 0xffffffffu, RR[t] = 0u;
             uint32_t prev = 0xffffffffu, prevlow = 0x100u;
             uint32_t* sp = scr;
+            // XW: window of Wr k-mers ending at e = min over the sub-windows (W k-mers) ending at
+            // e, e - W, ..., e - (T-1) W and e - (Wr - W); consecutive ones overlap or abut
+            const uint32_t Dmax = Wr - W, T = XW ? (Wr + W - 1) / W - 1 : 0u;
+            const uint32_t rmask = XW ? fast_ring_rows(Wr) - 1u : 0u;
+            uint32_t tL[4] = {0, 0, 0, 0}, tR[4] = {0, 0, 0, 0};
             // ambiguity: only threads whose stretch holds an ambiguous base do any work per block
             bool amb_here = false;
             uint32_t zrun = 0, pclean = 0;
@@ -310,6 +345,28 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
 #pragma unroll
                 for (int t = 0; t < W; t += 2) {
                     const bool two = t + 1 < W;
+                    if (XW && (t & 3) == 0) {
+                        // taps of k-mers t .. t+3: sub-window minima that ended i*W (i < T) and
+                        // Wr - W k-mers earlier; they were written >= 16 k-mers ago
+#pragma unroll
+                        for (int u = 0; u < 4; u++) tL[u] = 0xffffffffu, tR[u] = 0u;
+                        for (uint32_t i = 1; i <= T; i++) {
+                            const uint32_t d = i < T ? i * (uint32_t)W : Dmax;
+                            const uint32_t sbase = eb + o + t - d;
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (t + u < W) {
+                                    const uint32_t sl = (sbase + u) & rmask;
+                                    if (LR) {
+                                        const uint2 v = (reinterpret_cast<const uint2*>(r1) + lane)[(size_t)sl * 32];
+                                        tL[u] = min(tL[u], v.x), tR[u] = max(tR[u], v.y);
+                                    } else {
+                                        tL[u] = min(tL[u], r1[(size_t)sl * 32 + lane]);
+                                    }
+                                }
+                            }
+                        }
+                    }
                     const uint32_t word = N[(t >> 4) * 2 + ((t >> 1) & 1)];
                     const uint32_t idx = get_byte(word, (t & 15) >> 2);
                     const uint32_t addr = idx * (16u * FAST_TC) + tb;
@@ -369,6 +426,25 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                         if (two) mR1 = t + 2 < W ? max(preR, s2) : preR;
                         RR[t] = re0;
                         if (two) RR[t + 1] = re1;
+                    }
+                    if (XW) {
+                        // level 1 -> ring (read back Dmax .. k-mers later), level 2 = minimum with
+                        // the taps fetched at the head of this group of four
+                        const uint32_t s0 = (eb + o + t) & rmask, s1 = (eb + o + t + 1) & rmask;
+                        if (LR) {
+                            uint2* const row = reinterpret_cast<uint2*>(r1) + lane;
+                            row[(size_t)s0 * 32] = make_uint2(res0, mR0);
+                            if (two) row[(size_t)s1 * 32] = make_uint2(res1, mR1);
+                            mR0 = max(mR0, tR[t & 3]);
+                            if (two) mR1 = max(mR1, tR[(t + 1) & 3]);
+                        } else {
+                            r1[(size_t)s0 * 32 + lane] = res0;
+                            if (two) r1[(size_t)s1 * 32 + lane] = res1;
+                        }
+                        res0 = min(res0, tL[t & 3]);
+                        if (two) res1 = min(res1, tL[(t + 1) & 3]);
+                    }
+                    if (LR) {
                         accR[(o + t) >> 2] = put_byte(accR[(o + t) >> 2], mR0, (o + t) & 3);
                         if (two) {
                             accR[(o + t + 1) >> 2] = put_byte(accR[(o + t + 1) >> 2], mR1, (o + t + 1) & 3);
@@ -417,8 +493,8 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                     for (int t = 0; t < SB; t++) {
                         uint32_t cur = get_byte(accL[t >> 2], t & 3);
                         const uint32_t rgt = get_byte(accR[t >> 2], t & 3);
-                        if (cur != rgt && eb + t >= (uint32_t)(W - 1)) {
-                            if (!window_prefers_left(wbase, sh0, wlim, 2u * (eb + t - (W - 1)), a.l)) {
+                        if (cur != rgt && eb + t >= Wr - 1u) {
+                            if (!window_prefers_left(wbase, sh0, wlim, 2u * (eb + t - (Wr - 1u)), a.l)) {
                                 cur = rgt;
                                 accL[t >> 2] = put_byte(accL[t >> 2], rgt, t & 3);
                                 if (t == SB - 1) prev = lastR ^ 0xffff0000u;
@@ -539,7 +615,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
             auto stageB = [&]() {
                 const uint32_t t2 = dA >> 16, b2 = (dA >> 5) & 0x7ffu, bit2 = dA & 31u, e = b2 * SB + bit2;
                 const uint32_t lowb = (wvA >> (8u * (bit2 & 3u))) & 0xffu;
-                const uint32_t jl = e - (W - 1);  // local window index of the owner
+                const uint32_t jl = e - (Wr - 1);  // local window index of the owner
                 const uint32_t local = minim ? jl + ((lowb - jl) & 0xffu) : jl;
                 // owner's local base 0 = tile base + t2*S (- has_prev, which only differs for
                 // the very first thread of the sequence)
@@ -597,7 +673,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                 const uint32_t t2 = dsc >> 16, b2 = (dsc >> 5) & 0x7ffu, bit2 = dsc & 31u, e = b2 * SB + bit2;
                 const uint32_t wv = __ldcg(scr0 + (size_t)(b2 * WQ + (bit2 >> 2)) * 32 + t2);
                 const uint32_t lowb = (wv >> (8u * (bit2 & 3u))) & 0xffu;
-                const uint32_t jl = e - (W - 1);  // local window index of the owner
+                const uint32_t jl = e - (Wr - 1);  // local window index of the owner
                 list[x] = (t2 << 27) | (((lowb - jl) & 0xffu) << 16) | jl;
             }
             __syncwarp();
@@ -639,12 +715,14 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
 // ---- host side ---------------------------------------------------------------------------
 struct FastPlan {
     uint32_t S = 0, num_tiles = 0, grid = 0, list_cap = 0;
-    size_t scratch_words_per_block = 0;
+    size_t scratch_words_per_block = 0;  // position-byte rows, per warp and buffer
+    size_t r1_words = 0;                 // XW: level-1 rows, per warp
 };
 
 // Geometry for the fast kernel; returns false when (k, w, ...) is outside its domain.
-inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan* pl) {
-    if (p.w > FAST_MAX_W) return false;
+inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan* pl, bool allow_xw = false) {
+    const bool xw = p.w > FAST_MAX_W;
+    if (xw && (!allow_xw || p.w > FAST_XW_MAX_W || getenv("MZ_NO_XW"))) return false;
     const char* env_s = getenv("MZ_FAST_S");
     const char* env_bps = getenv("MZ_FAST_BPS");
     const uint32_t bps = env_bps ? (uint32_t)atoi(env_bps) : FAST_BPS;  // resident blocks per SM
@@ -655,10 +733,10 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     } else {
         // long segments amortise the (k+w-2)-base warm-up; keep >= ~3 tiles per resident block
         uint64_t want = nwin / (slots * 3 * 32);
-        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), 310);
+        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), xw ? 310u + p.w : 310u);
         // a thread computes S + w k-mers in whole loop iterations of SB k-mers: pick S so that
         // the last iteration is full (S = NB*SB - w; 288 -> 304 for w = 19 was worth 3 %)
-        const uint32_t sb = fast_sb(p.w);
+        const uint32_t sb = fast_sb(fast_wt(p.w));
         uint32_t nb = std::max<uint32_t>(1, (s + p.w) / sb);
         while (nb * sb < p.w + 16) nb++;
         s = nb * sb - p.w;
@@ -673,7 +751,7 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     }
     s = std::max<uint32_t>(16, s);
     // flag words and staging lists live in shared memory: stay within FAST_SMEM_LIMIT
-    while (s > 16 + fast_sb(p.w) && fast_smem(s, p.w, fast_list_cap(s, p)) > FAST_SMEM_LIMIT) s -= fast_sb(p.w);
+    while (s > 16 + fast_sb(fast_wt(p.w)) && fast_smem(s, p.w, fast_list_cap(s, p)) > FAST_SMEM_LIMIT) s -= fast_sb(fast_wt(p.w));
     if ((uint64_t)s + p.w + 2 >= 65535 || fast_nb(s, p.w) >= 2048) return false;  // descriptor: 11-bit iteration
     const uint64_t Tt = (uint64_t)32 * s;
     const uint64_t tiles = (nwin + Tt - 1) / Tt;
@@ -683,13 +761,14 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     pl->num_tiles = (uint32_t)tiles;
     pl->grid = (uint32_t)std::min<uint64_t>((tiles + FAST_WARPS - 1) / FAST_WARPS, (uint64_t)sm_count * bps);
     pl->scratch_words_per_block = fast_scratch_words(s, p.w);
+    pl->r1_words = fast_r1_words(s, p.w, p.strand_tiebreak != 0);
     return true;
 }
 
-template <int W, bool HC, bool LR, bool SYNC, bool AMB = false>
+template <int W, bool HC, bool LR, bool SYNC, bool AMB = false, bool XW = false>
 inline int launch_fast_inst(uint32_t grid, const KArgs& a, cudaStream_t st) {
-    auto kern = mz_fast_kernel<W, HC, LR, SYNC, AMB>;
-    const size_t smem = fast_smem(a.S, W, a.list_cap);
+    auto kern = mz_fast_kernel<W, HC, LR, SYNC, AMB, XW>;
+    const size_t smem = fast_smem(a.S, XW ? a.w : (uint32_t)W, a.list_cap);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return MZ_ERR_CUDA;
@@ -726,6 +805,25 @@ int launch_fast_g1(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 int launch_fast_g2(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 int launch_fast_g3(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 
+// long windows (XW): instance of the sub-window length W = fast_wt(p.w) in 17..24
+template <int W>
+inline int launch_fast_xw_w(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
+    const bool sync = p.mode != MZ_MODE_MINIMIZER;
+    if (p.strand_tiebreak) {
+        return sync ? launch_fast_inst<W, true, true, true, false, true>(grid, a, st)
+                    : launch_fast_inst<W, true, true, false, false, true>(grid, a, st);
+    }
+    if (p.hash_canonical) {
+        return sync ? launch_fast_inst<W, true, false, true, false, true>(grid, a, st)
+                    : launch_fast_inst<W, true, false, false, false, true>(grid, a, st);
+    }
+    return sync ? launch_fast_inst<W, false, false, true, false, true>(grid, a, st)
+                : launch_fast_inst<W, false, false, false, false, true>(grid, a, st);
+}
+// defined in mz_fast_x{0,1}.cu (sub-window 17..20, 21..24)
+int launch_fast_x0(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+int launch_fast_x1(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
+
 // defined in mz_fast_a{0..3}.cu
 int launch_fast_a0(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 int launch_fast_a1(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
@@ -733,6 +831,10 @@ int launch_fast_a2(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 int launch_fast_a3(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 
 inline int launch_fast(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
+    if (p.w > FAST_MAX_W) {
+        if (a.amb) return MZ_ERR_UNSUPPORTED;
+        return fast_wt(p.w) <= 20 ? launch_fast_x0(p, grid, a, st) : launch_fast_x1(p, grid, a, st);
+    }
     if (a.amb) {
         switch ((p.w - 1) / 8) {
             case 0: return launch_fast_a0(p, grid, a, st);
