@@ -519,3 +519,32 @@ def test_batch_chunk_pipeline_seams(sm, oracle, monkeypatch, chunk):
     offs, pos, _, vals = sm.canonical_minimizers(21, 11).run_batch(packed, starts=starts[perm], lens=lens[perm])
     eo, ep, _, ev = _oracle_batch(oracle, packed, starts[perm], lens[perm], 21, 11, True, 0, False)
     assert np.array_equal(offs, eo) and np.array_equal(pos, ep) and np.array_equal(vals, ev)
+
+
+def test_long_windows_subwindow_path(sm, oracle):
+    """32 < w <= 255 runs on the W-specialised kernel as the minimum over shifted sub-windows
+    (one to ten ring taps); w >= 256 on the runtime-w kernel.  Window lengths on both sides of
+    every tap-count boundary, all builders, random and all-ties (homopolymer) input."""
+    rng = np.random.default_rng(77)
+    n = 60_000
+    packed = oracle.synth_packed(99, n + 8)
+    homo = np.zeros(n // 4 + 16, dtype=np.uint8)  # AAAA...: every window is one big tie
+    mixed = packed.copy()
+    mixed[2000:5000] = 0x55                       # a long CCCC... run inside random sequence
+    ws = [33, 34, 47, 48, 49, 50, 64, 65, 71, 72, 73, 96, 97, 120, 121, 128, 200, 254, 255, 256, 300]
+    for w in ws:
+        for canonical in (False, True):
+            k = int(rng.integers(1, 40))
+            if canonical and (k + w - 1) % 2 == 0:
+                k += 1
+            for mode in (0, 1, 2):
+                if mode == 2 and w % 2 == 0:
+                    continue
+                for data, off, nn in ((packed, 3, n), (mixed, 0, 30_011), (homo, 1, 9_000 + w)):
+                    _check_case(sm, oracle, data, off, nn, k, w, canonical, mode,
+                                kind="mul" if w % 3 == 0 else "nt")
+    # forward builder with a canonical hasher, and short inputs around l
+    for w in (33, 64, 255):
+        for nn in (w + 4, w + 5, 2 * w + 9, 5 * w):
+            _check_case(sm, oracle, packed, 2, nn, 5, w, False, 0, hash_canon=True)
+            _check_case(sm, oracle, packed, 2, nn, 5 if w % 2 else 6, w, True, 0)

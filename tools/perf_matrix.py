@@ -9,7 +9,8 @@ host, off = bench.synth_packed_range(bench.SEED, 0, n)
 d_in = torch.from_numpy(np.ascontiguousarray(host)).cuda()
 ctx = sm.Context()
 cases = [(21, 11, 0, 0, 0), (21, 11, 1, 0, 64), (31, 19, 1, 0, 64), (31, 5, 1, 0, 64), (15, 10, 0, 0, 0), (19, 19, 1, 0, 0), (11, 31, 1, 0, 64),
-         (31, 32, 0, 0, 0), (8, 3, 1, 0, 64), (5, 1, 1, 0, 64), (31, 11, 1, 1, 0), (31, 11, 1, 2, 0), (21, 41, 1, 0, 64), (31, 19, 1, 0, 0)]
+         (31, 32, 0, 0, 0), (8, 3, 1, 0, 64), (5, 1, 1, 0, 64), (31, 11, 1, 1, 0), (31, 11, 1, 2, 0), (21, 41, 1, 0, 64), (31, 19, 1, 0, 0),
+         (15, 50, 0, 0, 0), (31, 63, 1, 0, 64), (21, 101, 1, 0, 64), (21, 201, 1, 0, 64), (21, 301, 1, 0, 64)]
 for (k, w, canon, mode, vb) in cases:
     if canon and (k + w - 1) % 2 == 0: w += 1
     p = ffi.MzParams(); L.mz_params_nthash(C.byref(p), k, w, mode, canon); p.value_bits = vb
