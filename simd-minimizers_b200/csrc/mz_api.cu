@@ -1108,7 +1108,8 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     // the chosen kernel; otherwise reads are cut into pieces of S windows (each piece a thread,
     // seam rule as everywhere: one extra window on the left seeds the dedup comparison).
     const bool lr = p->strand_tiebreak != 0;
-    const bool fast = p->w <= mz::FAST_MAX_W;
+    // w > 32: sub-window (XW) instances of the fast kernel
+    const bool fast = p->w <= mz::FAST_MAX_W || (p->w <= mz::FAST_XW_MAX_W && !getenv("MZ_NO_XW"));
     uint32_t S_cap, NTg = 128;
     if (fast) {
         S_cap = 288;
@@ -1167,9 +1168,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         a.overflow = a.ticket + 1;
         a.tile_state = d.scratch.p + 2;
         if (fast) {
-            if ((r = d.rows.reserve(j.fp.scratch_words_per_block * j.fp.grid * mz::FAST_WARPS * 2))) return r;
+            if ((r = d.rows.reserve((j.fp.scratch_words_per_block * 2 + j.fp.r1_words) * j.fp.grid * mz::FAST_WARPS))) return r;
             a.scratch = d.rows.p;
             a.scratch_words_per_block = j.fp.scratch_words_per_block;
+            a.r1_words_per_warp = j.fp.r1_words;
             a.list_cap = j.fp.list_cap;
             r = mz::launch_fast(*p, j.fp.grid, a, d.stream);
         } else {
@@ -1234,6 +1236,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             j.fp.num_tiles = (uint32_t)tiles;
             j.fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * mz::FAST_BPS);
             j.fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
+            j.fp.r1_words = mz::fast_r1_words(S, p->w, lr);
             j.fp.list_cap = mz::fast_list_cap(S, *p);
             j.num_tiles = j.fp.num_tiles;
         } else {
