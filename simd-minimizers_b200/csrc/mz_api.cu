@@ -251,7 +251,7 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
     Plan pl;
     mz::FastPlan fp;
     int rc = MZ_OK;
-    if (mz::plan_fast(d.sm_count, p, wend - wbeg, &fp, /*allow_xw=*/a.amb == nullptr && a.n_reads == 0)) {
+    if (mz::plan_fast(d.sm_count, p, wend - wbeg, &fp, /*allow_xw=*/a.n_reads == 0)) {
         pl.fast = true;
         pl.S = fp.S;
         pl.num_tiles = fp.num_tiles;

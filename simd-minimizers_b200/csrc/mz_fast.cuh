@@ -158,7 +158,6 @@ __device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
 template <int W, bool HC, bool LR, bool SYNC, bool AMB = false, bool XW = false>
 __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
-    static_assert(!(XW && AMB), "no skip-ambiguous instances for long windows");
     constexpr int B = (int)fast_b(W);    // van-Herk blocks per loop iteration
     constexpr int SB = B * W;            // k-mers per loop iteration (<= 32)
     constexpr int WQ = (SB + 3) / 4;     // record words per iteration
@@ -809,6 +808,11 @@ int launch_fast_g3(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 template <int W>
 inline int launch_fast_xw_w(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
     const bool sync = p.mode != MZ_MODE_MINIMIZER;
+    if (a.amb) {  // skip-ambiguous: canonical builders only (src/lib.rs:451)
+        if (!p.strand_tiebreak) return MZ_ERR_NOT_CANONICAL;
+        return sync ? launch_fast_inst<W, true, true, true, true, true>(grid, a, st)
+                    : launch_fast_inst<W, true, true, false, true, true>(grid, a, st);
+    }
     if (p.strand_tiebreak) {
         return sync ? launch_fast_inst<W, true, true, true, false, true>(grid, a, st)
                     : launch_fast_inst<W, true, true, false, false, true>(grid, a, st);
@@ -832,7 +836,6 @@ int launch_fast_a3(const mz_params&, uint32_t, const KArgs&, cudaStream_t);
 
 inline int launch_fast(const mz_params& p, uint32_t grid, const KArgs& a, cudaStream_t st) {
     if (p.w > FAST_MAX_W) {
-        if (a.amb) return MZ_ERR_UNSUPPORTED;
         return fast_wt(p.w) <= 20 ? launch_fast_x0(p, grid, a, st) : launch_fast_x1(p, grid, a, st);
     }
     if (a.amb) {
