@@ -263,7 +263,13 @@ __device__ __forceinline__ unsigned long long lookback_excl(unsigned long long* 
     unsigned long long excl = 0;
     if (tile != 0) {
         int64_t base = (int64_t)tile - 1;
-        while (true) {
+        // First step: the 32 nearest predecessors (in steady state one of them already holds an
+        // inclusive prefix).  If none does -- the first wave of a launch, where every tile's
+        // prefix depends on all tiles before it -- continue 256 descriptors at a time, eight
+        // independent loads per lane, so the chain is tile/256 L2 round trips instead of tile/32.
+        constexpr int K = 8;
+        bool found = false;
+        {
             int64_t idx = base - (int64_t)lane;
             unsigned long long v = 2ull;  // virtual tile before 0: inclusive prefix 0
             if (idx >= 0) {
@@ -273,14 +279,43 @@ __device__ __forceinline__ unsigned long long lookback_excl(unsigned long long* 
                     v = ld_state(state + idx);
                 }
             }
-            uint32_t is_prefix = __ballot_sync(0xffffffffu, (v & 3ull) == 2ull);
-            uint32_t first = is_prefix ? (uint32_t)__ffs(is_prefix) - 1u : 32u;
+            const uint32_t is_prefix = __ballot_sync(0xffffffffu, (v & 3ull) == 2ull);
+            const uint32_t first = is_prefix ? (uint32_t)__ffs(is_prefix) - 1u : 32u;
             unsigned long long contrib = (lane <= first) ? (v >> 2) : 0ull;
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
             excl += contrib;
-            if (is_prefix) break;
+            found = is_prefix != 0u;
             base -= 32;
+        }
+        while (!found) {
+            unsigned long long v[K];
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const int64_t idx = base - (int64_t)lane - 32 * j;
+                v[j] = idx >= 0 ? ld_state(state + idx) : 2ull;
+            }
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                const int64_t idx = base - (int64_t)lane - 32 * j;
+                while ((v[j] & 3ull) == 0ull) {
+                    __nanosleep(64);
+                    v[j] = ld_state(state + idx);
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < K; j++) {
+                if (!found) {
+                    const uint32_t is_prefix = __ballot_sync(0xffffffffu, (v[j] & 3ull) == 2ull);
+                    const uint32_t first = is_prefix ? (uint32_t)__ffs(is_prefix) - 1u : 32u;
+                    unsigned long long contrib = (lane <= first) ? (v[j] >> 2) : 0ull;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) contrib += __shfl_xor_sync(0xffffffffu, contrib, o);
+                    excl += contrib;
+                    found = is_prefix != 0u;
+                }
+            }
+            base -= 32 * K;
         }
     }
     if (lane == 0) st_state(state + tile, ((excl + total) << 2) | 2ull);

@@ -730,13 +730,17 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     if (env_s) {
         s = (uint32_t)atoi(env_s);
     } else {
-        // long segments amortise the (k+w-2)-base warm-up; keep >= ~3 tiles per resident block
-        uint64_t want = nwin / (slots * 3 * 32);
-        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), xw ? 310u + p.w : 310u);
+        // long segments amortise the (k+w-2)-base warm-up.  Few waves (small inputs, shards of a
+        // multi-GPU run): equal tiles in a whole number of waves, m = 1 .. 8 tiles per warp.
+        const uint32_t smax = xw ? 310u + p.w : 310u;
+        const uint64_t per_wave = slots * 32;
+        const uint64_t m = (nwin + per_wave * smax - 1) / (per_wave * smax);
+        const uint64_t want = m <= 8 ? (nwin + per_wave * m - 1) / (per_wave * m) : smax;
+        s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), smax);
         // a thread computes S + w k-mers in whole loop iterations of SB k-mers: pick S so that
         // the last iteration is full (S = NB*SB - w; 288 -> 304 for w = 19 was worth 3 %)
         const uint32_t sb = fast_sb(fast_wt(p.w));
-        uint32_t nb = std::max<uint32_t>(1, (s + p.w) / sb);
+        uint32_t nb = std::max<uint32_t>(1, (s + p.w + (m <= 8 ? sb - 1 : 0)) / sb);  // few waves: round up
         while (nb * sb < p.w + 16) nb++;
         s = nb * sb - p.w;
         // dense outputs: shorten the segments until a tile's expected entries fit one staging
