@@ -1234,7 +1234,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
             j.fp.S = S;
             j.fp.num_tiles = (uint32_t)tiles;
-            j.fp.grid = (uint32_t)std::min<uint64_t>((tiles + mz::FAST_WARPS - 1) / mz::FAST_WARPS, (uint64_t)d.sm_count * mz::FAST_BPS);
+            j.fp.grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * mz::FAST_BPS);
             j.fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
             j.fp.r1_words = mz::fast_r1_words(S, p->w, lr);
             j.fp.list_cap = mz::fast_list_cap(S, *p);

@@ -762,7 +762,9 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     pl->S = s;
     pl->list_cap = fast_list_cap(s, p);
     pl->num_tiles = (uint32_t)tiles;
-    pl->grid = (uint32_t)std::min<uint64_t>((tiles + FAST_WARPS - 1) / FAST_WARPS, (uint64_t)sm_count * bps);
+    // one block per SM as soon as there are that many tiles (warps take tiles from the ticket
+    // counter, so a small launch spreads over all SMs instead of filling a few of them)
+    pl->grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)sm_count * bps);
     pl->scratch_words_per_block = fast_scratch_words(s, p.w);
     pl->r1_words = fast_r1_words(s, p.w, p.strand_tiebreak != 0);
     return true;
