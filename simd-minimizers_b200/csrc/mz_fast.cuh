@@ -126,7 +126,9 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
 __device__ __forceinline__ void or_if_ne(uint32_t& bf, uint32_t a, uint32_t b, uint32_t bit) {
     asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bf) : "r"(a), "r"(b), "r"(bit));
 }
-// a*b + c issued as IMAD (FMA pipe) -- `b` is an opaque 1 so ptxas cannot turn it into an ALU add
+// a*b + c written as mad.lo in PTX, b = 1 from a volatile mov.  ptxas still picks the pipe per
+// use, but with plain C++ adds for the positions it allocates 128 instead of 115 registers and
+// the w = 31 instance runs 19 % slower (measured), so the positions stay expressed this way.
 __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -393,7 +395,6 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                             fw = fA;
                         }
                     }
-                    // positions: eb + t on the FMA pipe (IMAD with an opaque 1), the ALU pipe is the bottleneck
                     const uint32_t pos0 = imad(eb, one, o + t), pos1 = imad(eb, one, o + t + 1);
                     const uint32_t le0 = (h0 & 0xffff0000u) | pos0, le1 = (h1 & 0xffff0000u) | pos1;
                     uint32_t res0, res1 = 0, mR0 = 0, mR1 = 0;
