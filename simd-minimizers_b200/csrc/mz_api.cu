@@ -855,8 +855,22 @@ static int run_host_impl(mz_ctx* ctx, const mz_params* p, const uint8_t* packed,
     }
 
     struct Shard {
-        uint64_t wb, we, cap, count, abyte_lo = 0;
-        size_t anbytes = 0;
+        uint64_t wb, we, cap, count, byte_lo = 0, abyte_lo = 0;
+        size_t nbytes = 0, anbytes = 0;
+    };
+    // (re)launch shard s on its device with the output capacity s.cap
+    auto launch_shard = [&](DevState& d, Shard& s) -> int {
+        int r;
+        if ((r = d.pos.reserve(s.cap))) return r;
+        if (p->want_sk && (r = d.sk.reserve(s.cap))) return r;
+        if (vw && (r = d.val.reserve(s.cap * vw))) return r;
+        mz::KArgs a{};
+        fill_input_args(a, *p, d.in.p, bp_offset, s.byte_lo, s.nbytes, nwin);
+        if (am.bits) fill_amb_args(a, am, d.amb.p, s.abyte_lo, s.anbytes);
+        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = s.cap;
+        if ((r = enqueue_run(d, *p, a, s.wb, s.we, &ctx->timing.kernel_launches))) return r;
+        CK(cudaEventRecord(d.ev[2], d.stream));
+        return MZ_OK;
     };
     std::vector<Shard> sh(ndev);
     const uint64_t per = (nwin + ndev - 1) / ndev;
@@ -872,30 +886,14 @@ static int run_host_impl(mz_ctx* ctx, const mz_params* p, const uint8_t* packed,
         // bases [blo, bhi) of the sequence are needed: one extra window on the left
         const uint64_t blo = s.wb > 0 ? s.wb - 1 : 0;
         const uint64_t bhi = s.we + l - 1;
-        const uint64_t byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
-        const uint64_t byte_hi = (bp_offset + bhi + 3) / 4;
-        const size_t nbytes = byte_hi - byte_lo;
-        if ((rc = d.in.reserve(nbytes + 64))) return rc;
-        if ((rc = d.pos.reserve(s.cap))) return rc;
-        if (p->want_sk && (rc = d.sk.reserve(s.cap))) return rc;
-        if (vw && (rc = d.val.reserve(s.cap * vw))) return rc;
+        s.byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
+        s.nbytes = (size_t)((bp_offset + bhi + 3) / 4 - s.byte_lo);
+        if ((rc = d.in.reserve(s.nbytes + 64))) return rc;
         CK(cudaEventRecord(d.ev[0], d.stream));
-        CK(cudaMemcpyAsync(d.in.p, packed + byte_lo, nbytes, cudaMemcpyHostToDevice, d.stream));
+        CK(cudaMemcpyAsync(d.in.p, packed + s.byte_lo, s.nbytes, cudaMemcpyHostToDevice, d.stream));
         if (am.bits && (rc = upload_amb(d, am, blo, bhi, &s.abyte_lo, &s.anbytes))) return rc;
         CK(cudaEventRecord(d.ev[1], d.stream));
-        mz::KArgs a{};
-        fill_hash_args(a, *p);
-        a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
-        a.bitbias = (int64_t)(2 * bp_offset) - (int64_t)(8 * byte_lo);
-        a.seq_nwords = (nbytes + 3) / 4;
-        a.nwin = nwin;
-        if (am.bits) fill_amb_args(a, am, d.amb.p, s.abyte_lo, s.anbytes);
-        a.pos = d.pos.p;
-        a.sk = d.sk.p;
-        a.val = d.val.p;
-        a.cap = s.cap;
-        if ((rc = enqueue_run(d, *p, a, s.wb, s.we, &ctx->timing.kernel_launches))) return rc;
-        CK(cudaEventRecord(d.ev[2], d.stream));
+        if ((rc = launch_shard(d, s))) return rc;
     }
     // phase 2: counts; re-run a shard whose capacity estimate was too small
     uint64_t total = 0;
@@ -907,25 +905,7 @@ static int run_host_impl(mz_ctx* ctx, const mz_params* p, const uint8_t* packed,
         s.count = d.hs->count;
         if (d.hs->overflow) {
             s.cap = s.count;
-            if ((rc = d.pos.reserve(s.cap))) return rc;
-            if (p->want_sk && (rc = d.sk.reserve(s.cap))) return rc;
-            if (vw && (rc = d.val.reserve(s.cap * vw))) return rc;
-            const uint64_t blo = s.wb > 0 ? s.wb - 1 : 0;
-            const uint64_t byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
-            const uint64_t byte_hi = (bp_offset + s.we + l - 1 + 3) / 4;
-            mz::KArgs a{};
-            fill_hash_args(a, *p);
-            a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
-            a.bitbias = (int64_t)(2 * bp_offset) - (int64_t)(8 * byte_lo);
-            a.seq_nwords = (byte_hi - byte_lo + 3) / 4;
-            a.nwin = nwin;
-            if (am.bits) fill_amb_args(a, am, d.amb.p, s.abyte_lo, s.anbytes);
-            a.pos = d.pos.p;
-            a.sk = d.sk.p;
-            a.val = d.val.p;
-            a.cap = s.cap;
-            if ((rc = enqueue_run(d, *p, a, s.wb, s.we, &ctx->timing.kernel_launches))) return rc;
-            CK(cudaEventRecord(d.ev[2], d.stream));
+            if ((rc = launch_shard(d, s))) return rc;
             CK(cudaStreamSynchronize(d.stream));
             if (d.hs->overflow) {
                 g_last_error = "internal: exact-capacity re-run overflowed";
