@@ -182,14 +182,28 @@ int plan_generic(const DevState& d, const mz_params& p, uint64_t nwin, Plan* pl)
         NT = 64;
         global_ring = true;
     }
+    // Long windows: a ring of w entries per thread in shared memory leaves room for very few
+    // windows per thread (w = 301: S = 32, an 11x halo, 2.8 Gbp/s).  A ring in the L2-resident
+    // global scratch with 128 threads and S = 352 measured 17 Gbp/s (w = 301), 6.3 (w = 1001).
+    if (p.w >= 256 && !getenv("MZ_GENERIC_SMEM_RING")) {
+        NT = 128;
+        global_ring = true;
+    }
+    if (const char* e = getenv("MZ_GENERIC_GRING")) {  // experiments: force the global ring
+        NT = (uint32_t)std::max(32, atoi(e));
+        global_ring = true;
+    }
     // target ~4 tiles per SM, S in [32, 512], multiple of 32
     uint64_t target_tiles = (uint64_t)d.sm_count * 4;
     uint64_t s = (nwin + target_tiles * NT - 1) / (target_tiles * NT);
-    uint32_t S = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s, 32), 512);
+    uint32_t S = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(s, 32), global_ring ? 352 : 512);
     S = round_up(S, 32);
     const uint32_t wring = global_ring ? 0u : p.w;  // ring entries held in shared memory
     while (S > 32 && generic_smem(NT, S, wring, lr) > budget / 2) S -= 32;
-    if (const char* e = getenv("MZ_GENERIC_S")) S = round_up(std::max(32, atoi(e)), 32);
+    if (const char* e = getenv("MZ_GENERIC_S")) {
+        S = round_up(std::max(32, atoi(e)), 32);
+        while (S > 32 && generic_smem(NT, S, wring, lr) > budget) S -= 32;
+    }
     if (S + p.w + 2 >= 65535) return MZ_ERR_UNSUPPORTED;
     pl->fast = false;
     pl->NT = NT;
