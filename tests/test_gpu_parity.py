@@ -548,3 +548,19 @@ def test_long_windows_subwindow_path(sm, oracle):
         for nn in (w + 4, w + 5, 2 * w + 9, 5 * w):
             _check_case(sm, oracle, packed, 2, nn, 5, w, False, 0, hash_canon=True)
             _check_case(sm, oracle, packed, 2, nn, 5 if w % 2 else 6, w, True, 0)
+
+
+def test_very_large_k(sm, oracle):
+    """k far beyond the value widths (hash warm-up of thousands of bases, halo several times the
+    segment), combined with short, long and runtime-w windows; positions only."""
+    n = 300_000
+    packed = oracle.synth_packed(3, n + 8)
+    for (k, w, canonical, mode) in ((501, 19, True, 0), (2001, 11, True, 0), (1000, 50, False, 0),
+                                    (777, 33, True, 1), (4097, 5, False, 2), (300, 300, False, 0),
+                                    (301, 301, True, 0)):
+        b = _builder(sm, k, w, canonical, mode)
+        pr = oracle.make_params(k, w, canonical=canonical, mode=mode)
+        for off, nn in ((1, n), (0, k + w + 5), (2, 3 * (k + w))):
+            want, _ = oracle.run(packed, off, nn, pr, "stream")
+            got = b.run_once(sm.PackedSeq(packed, off, nn))
+            assert np.array_equal(got, want), (k, w, canonical, mode, off, nn)
