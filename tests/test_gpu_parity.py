@@ -564,3 +564,39 @@ def test_very_large_k(sm, oracle):
             want, _ = oracle.run(packed, off, nn, pr, "stream")
             got = b.run_once(sm.PackedSeq(packed, off, nn))
             assert np.array_equal(got, want), (k, w, canonical, mode, off, nn)
+
+
+def test_concurrent_host_threads(sm, oracle):
+    """The reference is called from many rayon workers at once (bench/src/bin/paper.rs:442-459);
+    here every host thread owns an mz_ctx.  Four threads, different parameters, concurrent calls
+    (ctypes releases the GIL), results must equal the single-threaded ones."""
+    import threading
+
+    n = 3_000_000
+    packed = oracle.synth_packed(17, n + 8)
+    cases = [(31, 19, True, 0), (21, 11, False, 0), (15, 41, True, 1), (9, 5, False, 2)]
+    expect = []
+    for (k, w, c, mode) in cases:
+        pr = oracle.make_params(k, w, canonical=c, mode=mode)
+        expect.append(oracle.run(packed, 1, n, pr, "stream")[0])
+    errors = []
+
+    def worker(i):
+        try:
+            k, w, c, mode = cases[i]
+            ctx = sm.Context()
+            b = _builder(sm, k, w, c, mode).context(ctx)
+            for _ in range(5):
+                got = b.run_once(sm.PackedSeq(packed, 1, n))
+                if not np.array_equal(got, expect[i]):
+                    errors.append((i, "mismatch"))
+            ctx.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((i, repr(e)))
+
+    ts = [threading.Thread(target=worker, args=(i,)) for i in range(len(cases))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errors, errors
