@@ -1,6 +1,8 @@
-# e2e (pinned host in/out through mz_run) vs chunk size of the pipelined host path, C2
-run() { echo -n "$*: "; env "$@" python bench.py --steps 4 --warmup 2 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['e2e']['ms_per_step'],2),'ms', round(d['e2e']['value'],1),'Gbp/s')"; }
-run MZ_CHUNK_WINDOWS=129166666
-run MZ_CHUNK_WINDOWS=64583333
-run MZ_CHUNK_WINDOWS=33554432
-run MZ_CHUNK_WINDOWS=258333333
+# S sweep (windows per thread) of the fast kernel, C2 3.1 Gbp device-resident
+run() { echo -n "$*: "; env "$@" python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; }
+run MZ_FAST_S=285
+run MZ_FAST_S=304
+run MZ_FAST_S=323
+run MZ_FAST_S=342
+run MZ_FAST_S=361
+run MZ_FAST_S=380
