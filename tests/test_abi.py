@@ -96,3 +96,21 @@ def test_host_mirror_api_surface(sm):
     assert [s.as_slice().get(i) for i in range(4)] == [0, 1, 3, 2]
     rc = s.as_slice().to_revcomp()
     assert [rc.as_slice().get(i) for i in range(3)] == [2, 1, 1]   # T C C = revcomp of ...GGA
+
+
+def test_header_is_plain_c_and_example_links(tmp_path):
+    """include/mz_b200.h must be usable from C (the FFI boundary): the C99 example compiles with
+    -pedantic and links against libmzb200.so (running it needs a GPU: tests/test_gpu_parity.py)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "simd-minimizers_b200")
+    if not os.path.exists(os.path.join(lib, "libmzb200.so")):
+        import __graft_entry__ as g
+
+        g.build()
+    exe = str(tmp_path / "minimal")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic",
+                           "-I", os.path.join(root, "include"), os.path.join(root, "examples", "minimal.c"),
+                           "-L", lib, "-lmzb200", "-Wl,-rpath," + lib, "-o", exe])
+    assert os.path.exists(exe)

@@ -600,3 +600,17 @@ def test_concurrent_host_threads(sm, oracle):
     for t in ts:
         t.join()
     assert not errors, errors
+
+
+def test_c_example_runs(tmp_path):
+    """examples/minimal.c (plain C99 caller of the ABI) reproduces the README vector."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    lib = os.path.join(root, "simd-minimizers_b200")
+    exe = str(tmp_path / "minimal")
+    subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "examples", "minimal.c"), "-L", lib, "-lmzb200",
+                           "-Wl,-rpath," + lib, "-o", exe])
+    out = subprocess.check_output([exe]).decode()
+    assert "pos 15 value 817" in out
