@@ -135,7 +135,8 @@ struct DevState {
     DevBuf<uint64_t> rstart;
     DevBuf<uint32_t> rlen;
     DevBuf<uint32_t> pread, pwin;  // batch pieces of long reads
-    HostScalars* hs = nullptr;
+    HostScalars* hs = nullptr;      // mapped pinned memory: the kernels write count / overflow here
+    HostScalars* hs_dev = nullptr;  // device address of hs
     PinBuf st_in, st_pos, st_sk, st_val, st_amb;  // pinned bounce buffers (pageable callers)
     PinBuf st_offs;                               // batch: chunk-local CSR offsets on their way out
 };
@@ -258,8 +259,18 @@ int launch_generic(const mz_params& p, const Plan& pl, const mz::KArgs& a, cudaS
     return MZ_OK;
 }
 
+// Point the kernel at the mapped host scalars and clear them (the previous launch that used this
+// DevState has been retired by the caller).
+void attach_host_scalars(DevState& d, mz::KArgs& a) {
+    d.hs->count = 0;
+    d.hs->ticket = 0;
+    d.hs->overflow = 0;
+    a.h_count = &d.hs_dev->count;
+    a.h_overflow = &d.hs_dev->overflow;
+}
+
 // Enqueue one launch producing windows [wbeg, wend) on d.stream.  Input is already on the
-// device (a.seq etc. filled by the caller).  Scalars are copied to d.hs; caller synchronises.
+// device (a.seq etc. filled by the caller).  Count / overflow land in d.hs; caller synchronises.
 int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uint64_t wend,
                 uint32_t* launches) {
     Plan pl;
@@ -294,6 +305,7 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
     a.ticket = reinterpret_cast<uint32_t*>(d.scratch.p + 1);
     a.overflow = a.ticket + 1;
     a.tile_state = d.scratch.p + 2;
+    attach_host_scalars(d, a);
     if (pl.fast) rc = mz::launch_fast(p, fp.grid, a, d.stream);
     else rc = launch_generic(p, pl, a, d.stream);
     if (rc > 0 && rc != MZ_OK) {
@@ -301,7 +313,6 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
         return rc;
     }
     if (launches) (*launches)++;
-    CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
     return MZ_OK;
 }
 
@@ -319,7 +330,8 @@ cudaError_t init_devstate(DevState& d, int device) {
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
     for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
-    if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable);
+    if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable | cudaHostAllocMapped);
+    if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&d.hs_dev, d.hs, 0);
     int v = 0;
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
     d.sm_count = v;
@@ -1161,6 +1173,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         a.ticket = reinterpret_cast<uint32_t*>(d.scratch.p + 1);
         a.overflow = a.ticket + 1;
         a.tile_state = d.scratch.p + 2;
+        attach_host_scalars(d, a);
         if (fast) {
             if ((r = d.rows.reserve((j.fp.scratch_words_per_block * 2 + j.fp.r1_words) * j.fp.grid * mz::FAST_WARPS))) return r;
             a.scratch = d.rows.p;
@@ -1178,7 +1191,6 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             return r;
         }
         ctx->timing.kernel_launches++;
-        CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
         return MZ_OK;
     };
 

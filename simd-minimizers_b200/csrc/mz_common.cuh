@@ -33,6 +33,10 @@ struct KArgs {
     unsigned long long* tile_state;  // decoupled look-back descriptors, zeroed before launch
     uint32_t* ticket;                // dynamic tile id counter, zeroed before launch
     unsigned long long* count_out;   // total entries produced by this launch
+    // the same two results written straight into mapped pinned host memory (no D2H copy node
+    // after the kernel: one stream operation less per launch); zeroed by the host before launch
+    unsigned long long* h_count;
+    uint32_t* h_overflow;
     uint32_t* overflow;              // set to 1 when cap was too small
     uint32_t num_tiles;
     uint32_t* scratch;                 // fast kernel: per-warp record rows (L2-resident); generic: global ring

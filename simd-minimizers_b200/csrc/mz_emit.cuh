@@ -112,13 +112,19 @@ __device__ __forceinline__ void emit_phase(const KArgs& a, const Segment& sg, ui
         unsigned long long g = lookback_warp0(a.tile_state, tile, total);
         if (tid == 0) {
             s_gbase = g;
-            if (tile == a.num_tiles - 1) *a.count_out = g + total;
+            if (tile == a.num_tiles - 1) {
+                *a.count_out = g + total;
+                if (a.h_count) *a.h_count = g + total;
+            }
         }
     }
     __syncthreads();
     const unsigned long long gbase = s_gbase;
     const bool ovf = gbase + total > a.cap;
-    if (ovf && tid == 0) *a.overflow = 1u;
+    if (ovf && tid == 0) {
+        *a.overflow = 1u;
+        if (a.h_overflow) *a.h_overflow = 1u;
+    }
     if (a.n_reads != 0) write_csr_offset(a, (uint64_t)tile * NT + tid, gbase + toff + cnt);
     if (ovf || total == 0) return;
 

@@ -559,9 +559,15 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
         const uint32_t total = __shfl_sync(0xffffffffu, inc_e, 31);
         const uint32_t toff = inc_e - cnt_e;
         const unsigned long long gbase = lookback_excl(a.tile_state, tile_e, total);
-        if (lane == 0 && tile_e == a.num_tiles - 1) *a.count_out = gbase + total;
+        if (lane == 0 && tile_e == a.num_tiles - 1) {
+            *a.count_out = gbase + total;
+            if (a.h_count) *a.h_count = gbase + total;
+        }
         const bool ovf = gbase + total > a.cap;
-        if (ovf && lane == 0) *a.overflow = 1u;
+        if (ovf && lane == 0) {
+            *a.overflow = 1u;
+            if (a.h_overflow) *a.h_overflow = 1u;
+        }
         if (a.n_reads != 0) write_csr_offset(a, (uint64_t)tile_e * 32u + lane, gbase + inc_e);
         if (!ovf && total != 0) {
 

@@ -1,8 +1,6 @@
-# S sweep (windows per thread) of the fast kernel, C2 3.1 Gbp device-resident
-run() { echo -n "$*: "; env "$@" python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['value'])"; }
-run MZ_FAST_S=285
-run MZ_FAST_S=304
-run MZ_FAST_S=323
-run MZ_FAST_S=342
-run MZ_FAST_S=361
-run MZ_FAST_S=380
+# small inputs / shards: time per launch for a range of sizes (forward k=21 w=11 and C2 parameters)
+for n in 10000000 100000000 387500000 3100000000; do
+  for c in c1 c2; do
+    echo -n "config $c n=$n: "; python bench.py --config $c --n-bases $n --steps 10 --warmup 5 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(round(d['ms_per_step']*1000,1),'us', round(d['value'],1),'Gbp/s')"
+  done
+done
