@@ -261,7 +261,12 @@ int launch_generic(const mz_params& p, const Plan& pl, const mz::KArgs& a, cudaS
 
 // Point the kernel at the mapped host scalars and clear them (the previous launch that used this
 // DevState has been retired by the caller).
+bool hs_by_copy() {  // experiments: MZ_HS_COPY=1 restores the D2H copy of the scalars
+    static const bool v = getenv("MZ_HS_COPY") != nullptr;
+    return v;
+}
 void attach_host_scalars(DevState& d, mz::KArgs& a) {
+    if (hs_by_copy()) return;
     d.hs->count = 0;
     d.hs->ticket = 0;
     d.hs->overflow = 0;
@@ -313,6 +318,7 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
         return rc;
     }
     if (launches) (*launches)++;
+    if (hs_by_copy()) CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
     return MZ_OK;
 }
 
@@ -1191,6 +1197,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             return r;
         }
         ctx->timing.kernel_launches++;
+        if (hs_by_copy()) CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
         return MZ_OK;
     };
 
