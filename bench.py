@@ -400,6 +400,15 @@ def main():
             line["e2e"] = {"value": n / (e2e_ms_max * 1e-3) / 1e9, "unit": "Gbp/s",
                            "ms_per_step": e2e_ms_max, "h2d_bytes_per_step": int(h2d_bytes),
                            "d2h_bytes_per_step": int(d2h_bytes)}
+            # d2h_bytes_per_step = bytes delivered into the caller's host arrays.  Positions and
+            # super-k-mer starts of minimizer runs (w <= 127) cross PCIe delta-coded (1 byte per
+            # entry + a u32 per 256 entries, decoded by mz_run while it fills the arrays), so
+            # fewer bytes are on the wire; MZ_NO_POS_DELTA=1 disables the codec.
+            if cfg["mode"] == 0 and cfg["w"] <= 127 and not os.environ.get("MZ_NO_POS_DELTA"):
+                narr = 1 + int(cfg["want_sk"])
+                wire = tot_count * (8 * vw) + narr * (tot_count + 4 * ((tot_count + 255) // 256))
+                line["e2e"]["d2h_wire_bytes_per_step"] = int(wire)
+                line["e2e"]["d2h_codec"] = "pos/sk as int8 deltas + u32 base per 256 entries"
         if world == 1 and not args.no_cpu_baseline:
             threads = len(os.sched_getaffinity(0))
             sample = min(n, 32_000_000 * max(1, threads // 2))

@@ -139,11 +139,13 @@ struct DevState {
     HostScalars* hs_dev = nullptr;  // device address of hs
     PinBuf st_in, st_pos, st_sk, st_val, st_amb;  // pinned bounce buffers (pageable callers)
     PinBuf st_offs;                               // batch: chunk-local CSR offsets on their way out
+    DevBuf<uint8_t> delta;                        // delta-coded pos / sk of a chunk (transfer codec)
+    PinBuf st_delta;
 };
 
 }  // namespace
 
-constexpr int kSlots = 3;  // chunks in flight per device in the pipelined host path
+constexpr int kSlots = 4;  // chunks in flight per device in the pipelined host path
 
 struct mz_ctx {
     std::vector<DevState> devs;                 // slot 0 of every device
@@ -399,6 +401,57 @@ int upload_amb(DevState& d, const AmbSrc& am, uint64_t blo, uint64_t bhi, uint64
     return MZ_OK;
 }
 
+// ---- transfer codec for minimizer positions / super-k-mer starts --------------------------------
+// Consecutive minimizer positions differ by at most w in either direction (the strand rule can step
+// back inside a tie), consecutive super-k-mer starts by 1..w, so for w <= 127 a chunk's u32 array
+// crosses PCIe as one signed byte per entry plus an absolute u32 every 256 entries: 1.02 instead of
+// 4 bytes per entry (C2: 3.72 -> 2.8 GB of D2H per run).  The host adds the deltas up again while it
+// writes the caller's array (16 threads, a few ms per 3.1 Gbp, hidden behind the next chunk).
+constexpr uint32_t kDeltaBlock = 256;
+__global__ void mz_delta_encode_kernel(const uint32_t* __restrict__ v, uint64_t n,
+                                       int8_t* __restrict__ delta, uint32_t* __restrict__ base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if ((i & (kDeltaBlock - 1)) == 0) {
+        base[i / kDeltaBlock] = v[i];
+        delta[i] = 0;
+    } else {
+        delta[i] = (int8_t)(int32_t)(v[i] - v[i - 1]);
+    }
+}
+size_t delta_bytes(uint64_t n) {  // [deltas, padded to 4][bases]
+    return (size_t)((n + 3) & ~uint64_t(3)) + (size_t)((n + kDeltaBlock - 1) / kDeltaBlock) * 4;
+}
+void delta_decode(const unsigned char* enc, uint64_t n, uint32_t* out) {
+    const int8_t* delta = reinterpret_cast<const int8_t*>(enc);
+    const uint32_t* base = reinterpret_cast<const uint32_t*>(enc + ((n + 3) & ~uint64_t(3)));
+    const uint64_t nblk = (n + kDeltaBlock - 1) / kDeltaBlock;
+    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    if (nblk < 64) nt = 1;
+    auto work = [=](uint64_t b0, uint64_t b1) {
+        for (uint64_t b = b0; b < b1; b++) {
+            const uint64_t lo = b * kDeltaBlock, hi = std::min<uint64_t>(lo + kDeltaBlock, n);
+            uint32_t v = base[b];
+            out[lo] = v;
+            for (uint64_t i = lo + 1; i < hi; i++) {
+                v += (uint32_t)(int32_t)delta[i];
+                out[i] = v;
+            }
+        }
+    };
+    if (nt == 1) {
+        work(0, nblk);
+        return;
+    }
+    std::vector<std::thread> th;
+    const uint64_t per = (nblk + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+        const uint64_t b0 = std::min(nblk, (uint64_t)t * per), b1 = std::min(nblk, b0 + per);
+        if (b1 > b0) th.emplace_back(work, b0, b1);
+    }
+    for (auto& t : th) t.join();
+}
+
 // Single device, large input: windows are cut into chunks that flow through kSlots streams so
 // that the H2D copy of chunk c+2, the kernel of chunk c+1 and the D2H copy of chunk c overlap.
 // Chunks are seams like any other shard (one extra window on the left); outputs land in the
@@ -421,10 +474,13 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
     // (mz_host_alloc / cudaHostRegister'ed) memory is used directly.
     const bool page_in = is_pageable(packed);
     const bool page_out = is_pageable(out->pos) || (p.want_sk && is_pageable(out->sk)) || (vw && is_pageable(out->val));
+    // positions (and super-k-mer starts) of plain minimizer runs cross PCIe delta-coded
+    const bool delta = p.mode == MZ_MODE_MINIMIZER && p.w <= 127 && !am.bits && !getenv("MZ_NO_POS_DELTA");
     std::vector<Job> jobs(nchunks);
     uint64_t total = 0;
     bool too_small = false;
     int rc;
+    double dbg_sync_ms = 0;  // MZ_DEBUG_PIPE: time the calling thread waits for kernels
     CK(cudaSetDevice(ctx->devs[0].device));
 
     auto issue = [&](uint64_t c) -> int {
@@ -459,21 +515,56 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         CK(cudaEventRecord(d.ev[2], d.stream));
         return MZ_OK;
     };
-    // pageable outputs: copy a finished chunk from the bounce buffers into the caller's arrays
+    // D2H of chunk c enqueued -> a helper thread waits for it and writes the caller's arrays (delta
+    // decode / copy out of the bounce buffers), so the calling thread keeps the pipeline fed
+    std::thread helper[kSlots];
+    int helper_rc[kSlots] = {};
+    struct JoinAll {  // error paths return early: never destroy a joinable thread
+        std::thread* h;
+        ~JoinAll() {
+            for (int i = 0; i < kSlots; i++)
+                if (h[i].joinable()) h[i].join();
+        }
+    } join_all{helper};
+    auto join_helper = [&](int sl) -> int {
+        if (helper[sl].joinable()) helper[sl].join();
+        const int r = helper_rc[sl];
+        helper_rc[sl] = 0;
+        return r;
+    };
     auto finish = [&](uint64_t c) -> int {
-        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        const int sl = (int)(c % kSlots);
+        DevState& d = ctx->slot(0, sl);
         Job& j = jobs[c];
-        if (!j.staged || !j.count) return MZ_OK;
-        CK(cudaEventSynchronize(d.ev[3]));
-        parallel_memcpy(out->pos + j.out_off, d.st_pos.p, j.count * 4);
-        if (p.want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4);
-        if (vw) parallel_memcpy(out->val + j.out_off * vw, d.st_val.p, j.count * 8 * vw);
+        if (!(j.staged || delta) || !j.count || too_small) return MZ_OK;
+        int r = join_helper(sl);
+        if (r) return r;
+        const int device = ctx->devs[0].device;
+        const bool want_sk = p.want_sk != 0;
+        helper[sl] = std::thread([&d, &j, &helper_rc, sl, out, vw, delta, want_sk, device]() {
+            if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(d.ev[3]) != cudaSuccess) {
+                helper_rc[sl] = MZ_ERR_CUDA;
+                return;
+            }
+            if (delta) {
+                delta_decode(d.st_delta.p, j.count, out->pos + j.out_off);
+                if (want_sk) delta_decode(d.st_delta.p + delta_bytes(j.count), j.count, out->sk + j.out_off);
+            } else {
+                parallel_memcpy(out->pos + j.out_off, d.st_pos.p, j.count * 4);
+                if (want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4);
+            }
+            if (vw && j.staged) parallel_memcpy(out->val + j.out_off * vw, d.st_val.p, j.count * 8 * vw);
+        });
         return MZ_OK;
     };
     auto retire = [&](uint64_t c) -> int {
         DevState& d = ctx->slot(0, (int)(c % kSlots));
         Job& j = jobs[c];
-        CK(cudaStreamSynchronize(d.stream));
+        {
+            const auto ts0 = std::chrono::steady_clock::now();
+            CK(cudaStreamSynchronize(d.stream));
+            dbg_sync_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
+        }
         float h2d = 0, ker = 0;
         cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
         cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
@@ -502,27 +593,46 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         j.count = count;
         j.out_off = total;
         if (!too_small && count) {
+            // the slot's bounce buffers are about to be overwritten: its previous chunk must be out
+            if (int r = join_helper((int)(c % kSlots))) return r;
             uint32_t *hpos = out->pos + total, *hsk = p.want_sk ? out->sk + total : nullptr;
             uint64_t* hval = vw ? out->val + total * vw : nullptr;
             if (page_out) {
                 int r;
-                if ((r = d.st_pos.reserve(count * 4))) return r;
-                if (p.want_sk && (r = d.st_sk.reserve(count * 4))) return r;
+                if (!delta && (r = d.st_pos.reserve(count * 4))) return r;
+                if (!delta && p.want_sk && (r = d.st_sk.reserve(count * 4))) return r;
                 if (vw && (r = d.st_val.reserve(count * 8 * vw))) return r;
                 hpos = reinterpret_cast<uint32_t*>(d.st_pos.p);
                 hsk = reinterpret_cast<uint32_t*>(d.st_sk.p);
                 hval = reinterpret_cast<uint64_t*>(d.st_val.p);
                 j.staged = true;
             }
-            CK(cudaMemcpyAsync(hpos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
-            if (p.want_sk) CK(cudaMemcpyAsync(hsk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            if (delta) {
+                int r;
+                const size_t nb = delta_bytes(count), narr = p.want_sk ? 2 : 1;
+                if ((r = d.delta.reserve(nb * narr))) return r;
+                if ((r = d.st_delta.reserve(nb * narr))) return r;
+                const unsigned nt = 256, nblk = (unsigned)((count + nt - 1) / nt);
+                const size_t boff = (size_t)((count + 3) & ~uint64_t(3));
+                mz_delta_encode_kernel<<<nblk, nt, 0, d.stream>>>(d.pos.p, count, reinterpret_cast<int8_t*>(d.delta.p),
+                                                                 reinterpret_cast<uint32_t*>(d.delta.p + boff));
+                if (p.want_sk)
+                    mz_delta_encode_kernel<<<nblk, nt, 0, d.stream>>>(d.sk.p, count, reinterpret_cast<int8_t*>(d.delta.p + nb),
+                                                                     reinterpret_cast<uint32_t*>(d.delta.p + nb + boff));
+                CK(cudaGetLastError());
+                ctx->timing.kernel_launches += (uint32_t)narr;
+                CK(cudaMemcpyAsync(d.st_delta.p, d.delta.p, nb * narr, cudaMemcpyDeviceToHost, d.stream));
+            } else {
+                CK(cudaMemcpyAsync(hpos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+                if (p.want_sk) CK(cudaMemcpyAsync(hsk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+            }
             if (vw) CK(cudaMemcpyAsync(hval, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
             CK(cudaEventRecord(d.ev[3], d.stream));
         }
         total += count;
         return MZ_OK;
     };
-    if (!page_out) {
+    if (!page_out && !delta) {
         for (uint64_t c = 0; c < nchunks; c++) {
             if ((rc = issue(c))) return rc;
             if (c + 1 >= (uint64_t)kSlots && (rc = retire(c + 1 - kSlots))) return rc;
@@ -530,14 +640,22 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         for (uint64_t c = nchunks >= (uint64_t)kSlots ? nchunks - (kSlots - 1) : 0; c < nchunks; c++)
             if ((rc = retire(c))) return rc;
     } else {
-        // three stages in flight: kernel(c) | D2H(c-1) into the bounce buffers | memcpy(c-2)
-        for (uint64_t c = 0; c < nchunks + 2; c++) {
+        // stages in flight: H2D + kernel of chunks c, c-1 | D2H(c-2) | decode / copy-out(c-3) on a
+        // helper thread.  Issuing two chunks ahead keeps the calling thread from waiting for an
+        // H2D copy that it has only just enqueued.
+        constexpr uint64_t R = kSlots - 2, F = kSlots - 1;
+        for (uint64_t c = 0; c < nchunks + F; c++) {
             if (c < nchunks && (rc = issue(c))) return rc;
-            if (c >= 1 && c - 1 < nchunks && (rc = retire(c - 1))) return rc;
-            if (c >= 2 && (rc = finish(c - 2))) return rc;
+            if (c >= R && c - R < nchunks && (rc = retire(c - R))) return rc;
+            if (c >= F && (rc = finish(c - F))) return rc;
         }
     }
     for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(ctx->slot(0, sl).stream));
+    for (int sl = 0; sl < kSlots; sl++)
+        if (int r = join_helper(sl)) return r;
+    if (getenv("MZ_DEBUG_PIPE"))
+        fprintf(stderr, "[mz pipeline] chunks %llu delta %d: host waited %.1f ms for kernels\n",
+                (unsigned long long)nchunks, (int)delta, dbg_sync_ms);
     out->count = total;
     return too_small ? MZ_ERR_CAPACITY : MZ_OK;
 }
@@ -763,7 +881,7 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         if (d.stream) cudaStreamSynchronize(d.stream);
         d.scratch.release(), d.rows.release(), d.ascii.release(), d.in.release(), d.pos.release(), d.sk.release(), d.val.release();
         d.offs.release(), d.rstart.release(), d.rlen.release(), d.pread.release(), d.pwin.release();
-        d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release(), d.st_amb.release(), d.st_offs.release();
+        d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release(), d.st_amb.release(), d.st_offs.release(), d.st_delta.release(), d.delta.release();
         d.amb.release();
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
