@@ -402,8 +402,10 @@ int upload_amb(DevState& d, const AmbSrc& am, uint64_t blo, uint64_t bhi, uint64
 }
 
 // ---- transfer codec for minimizer positions / super-k-mer starts --------------------------------
-// Consecutive minimizer positions differ by at most w in either direction (the strand rule can step
-// back inside a tie), consecutive super-k-mer starts by 1..w, so for w <= 127 a chunk's u32 array
+// Entry i+1 is emitted at the first window j whose selection differs from window j-1's, which was
+// entry i's position p_i in [j-1, j+w-2]; the new position lies in [j, j+w-1], so
+// p_{i+1} - p_i is in [-(w-2), w] whatever the tie rule does, and a run of windows that all select
+// the same k-mer is at most w long, so consecutive super-k-mer starts differ by 1..w.  For w <= 127 a chunk's u32 array
 // crosses PCIe as one signed byte per entry plus an absolute u32 every 256 entries: 1.02 instead of
 // 4 bytes per entry (C2: 3.72 -> 2.8 GB of D2H per run).  The host adds the deltas up again while it
 // writes the caller's array (16 threads, a few ms per 3.1 Gbp, hidden behind the next chunk).

@@ -614,3 +614,36 @@ def test_c_example_runs(tmp_path):
                            "-Wl,-rpath," + lib, "-o", exe])
     out = subprocess.check_output([exe]).decode()
     assert "pos 15 value 817" in out
+
+
+def test_pipelined_transfer_codec(sm, oracle, monkeypatch):
+    """Positions / super-k-mer starts cross PCIe as int8 deltas in the chunk-pipelined mz_run
+    (minimizers, w <= 127).  Inputs that stress the codec: ties everywhere (homopolymer and
+    dinucleotide repeats: the strand rule steps backwards), the largest coded window (w = 127,
+    deltas up to +-127), the first window length that is copied verbatim (w = 128), entry counts
+    around the 256-entry block size, and the codec switched off gives the same arrays."""
+    monkeypatch.setenv("MZ_PIPELINE_MIN_WINDOWS", "1")
+    n = 300_000
+    rnd = oracle.synth_packed(23, n + 8)
+    homo = np.zeros(n // 4 + 16, dtype=np.uint8)                 # AAAA...
+    dinuc = np.full(n // 4 + 16, 0x11 * 0 + 0b01000100, dtype=np.uint8)  # ACAC...
+    tga = np.full(n // 4 + 16, 0b10110010, dtype=np.uint8)       # T A G T repeats: TG-rich / poor windows
+    mixed = rnd.copy()
+    mixed[1000:9000] = 0b11101110                                # long GTGT run inside random sequence
+    for chunk in ("1000", "70001"):
+        monkeypatch.setenv("MZ_CHUNK_WINDOWS", chunk)
+        for data in (rnd, homo, dinuc, tga, mixed):
+            for (k, w, c) in ((31, 19, True), (5, 127, True), (4, 127, False), (5, 128, False), (6, 3, False), (1, 1, True)):
+                if c and (k + w - 1) % 2 == 0:
+                    k += 1
+                _check_case(sm, oracle, data, 1, n, k, w, c, 0)
+    # tiny outputs: 0, 1, 255, 256, 257 entries per chunk
+    for nn in (60, 61, 300, 2600, 2700):
+        monkeypatch.setenv("MZ_CHUNK_WINDOWS", "100000")
+        _check_case(sm, oracle, rnd, 0, nn, 31, 19, True, 0)
+    # codec off == codec on
+    seq = sm.PackedSeq(mixed, 2, n)
+    a = sm.canonical_minimizers(21, 11).run_once(seq)
+    monkeypatch.setenv("MZ_NO_POS_DELTA", "1")
+    b = sm.canonical_minimizers(21, 11).run_once(seq)
+    assert np.array_equal(a, b)
