@@ -187,6 +187,13 @@ def cpu_port_run(cfg, sample_bases: int, threads: int):
 _CPU_CACHE: dict = {}
 
 
+def limit_host_threads(world: int) -> None:
+    """One rank per GPU shares the host: split its cores between the ranks' copy / decode threads."""
+    if world > 1 and "MZ_HOST_THREADS" not in os.environ:
+        cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        os.environ["MZ_HOST_THREADS"] = str(max(2, min(16, cores // world)))
+
+
 def run_reference(args, cfg, rank, world):
     """--impl reference: the reference's CPU algorithm (oracle port; kind='port' because the
     Rust crate cannot be compiled here) on all host threads, bounded sample per step."""
@@ -250,6 +257,7 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    limit_host_threads(world)  # before libmzb200 reads MZ_HOST_THREADS
     sm = importlib.import_module("simd-minimizers_b200")
     ffi = importlib.import_module("simd-minimizers_b200._ffi")
     L = ffi.lib()

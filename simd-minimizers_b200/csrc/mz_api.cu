@@ -95,9 +95,20 @@ bool is_pageable(const void* ptr) {
     return at.type == cudaMemoryTypeUnregistered;
 }
 
+// host threads used for bounce-buffer copies and delta decoding: 16 by default, MZ_HOST_THREADS
+// overrides (several processes sharing one host, e.g. one rank per GPU)
+unsigned host_threads() {
+    static const unsigned v = [] {
+        unsigned n = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+        if (const char* e = getenv("MZ_HOST_THREADS")) n = (unsigned)std::max(1, atoi(e));
+        return std::min(n, 64u);
+    }();
+    return v;
+}
+
 // memcpy split over a few host threads (a single thread cannot keep up with a Gen5 x16 link)
 void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    unsigned nt = host_threads();
     if (bytes < (8u << 20)) nt = 1;
     if (nt == 1) {
         memcpy(dst, src, bytes);
@@ -428,7 +439,7 @@ void delta_decode(const unsigned char* enc, uint64_t n, uint32_t* out) {
     const int8_t* delta = reinterpret_cast<const int8_t*>(enc);
     const uint32_t* base = reinterpret_cast<const uint32_t*>(enc + ((n + 3) & ~uint64_t(3)));
     const uint64_t nblk = (n + kDeltaBlock - 1) / kDeltaBlock;
-    unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+    unsigned nt = host_threads();
     if (nblk < 64) nt = 1;
     auto work = [=](uint64_t b0, uint64_t b1) {
         for (uint64_t b = b0; b < b1; b++) {
