@@ -554,7 +554,7 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         if (r) return r;
         const int device = ctx->devs[0].device;
         const bool want_sk = p.want_sk != 0;
-        helper[sl] = std::thread([&d, &j, &helper_rc, sl, out, vw, delta, want_sk, device]() {
+        auto work = [&d, &j, &helper_rc, sl, out, vw, delta, want_sk, device]() {
             if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(d.ev[3]) != cudaSuccess) {
                 helper_rc[sl] = MZ_ERR_CUDA;
                 return;
@@ -567,7 +567,15 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
                 if (want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4);
             }
             if (vw && j.staged) parallel_memcpy(out->val + j.out_off * vw, d.st_val.p, j.count * 8 * vw);
-        });
+        };
+        try {
+            helper[sl] = std::thread(work);
+        } catch (...) {  // no thread to be had: do it here (nothing may unwind across the C ABI)
+            work();
+            r = helper_rc[sl];
+            helper_rc[sl] = 0;
+            if (r) return r;
+        }
         return MZ_OK;
     };
     auto retire = [&](uint64_t c) -> int {
