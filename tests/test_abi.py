@@ -114,3 +114,18 @@ def test_header_is_plain_c_and_example_links(tmp_path):
                            "-I", os.path.join(root, "include"), os.path.join(root, "examples", "minimal.c"),
                            "-L", lib, "-lmzb200", "-Wl,-rpath," + lib, "-o", exe])
     assert os.path.exists(exe)
+
+
+def test_launch_geometry_invariants(tmp_path):
+    """tests/plan_test.cu: host-only checks of plan_fast for every window length 1..300, all
+    builders and input sizes from 1 to 2^32 windows (shared-memory limit, descriptor field widths,
+    whole-iteration segments, sub-window / ring rules of the long-window instances)."""
+    import subprocess
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "plan_test")
+    subprocess.check_call([os.environ.get("NVCC", "nvcc"), "-std=c++17", "-O1", "-gencode",
+                           "arch=compute_100a,code=sm_100a", "-o", exe,
+                           os.path.join(root, "tests", "plan_test.cu")])
+    env = {k: v for k, v in os.environ.items() if not k.startswith("MZ_")}
+    assert "plan ok" in subprocess.check_output([exe], env=env).decode()

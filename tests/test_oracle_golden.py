@@ -226,3 +226,34 @@ def test_skip_ambiguous_properties(oracle):
         pr = oracle.make_params(7, 5, canonical=True)
         assert np.array_equal(oracle.run_skip_ambiguous(packed, off, 500 - off, amb, off, pr),
                               oracle.run_skip_ambiguous(p2, 0, 500 - off, a2, 0, pr))
+
+
+def test_position_delta_bound(oracle):
+    """The PCIe transfer codec of mz_run stores consecutive positions / super-k-mer starts as int8
+    deltas for w <= 127.  The bound it relies on, checked on the oracle: p[i+1] - p[i] lies in
+    [-(w-2), w] (the strand rule may step back inside a tie) and sk[i+1] - sk[i] in [1, w]."""
+    rng = np.random.default_rng(9)
+    n = 20_000
+    seqs = [oracle.synth_packed(4, n + 8), np.zeros(n // 4 + 16, dtype=np.uint8),
+            np.full(n // 4 + 16, 0b01000100, dtype=np.uint8), np.full(n // 4 + 16, 0b10110010, dtype=np.uint8)]
+    mixed = seqs[0].copy()
+    mixed[500:1500] = 0b11101110
+    seqs.append(mixed)
+    saw_backward = False
+    for packed in seqs:
+        for _ in range(12):
+            k = int(rng.integers(1, 34))
+            w = int(rng.integers(1, 128))
+            canonical = bool(rng.integers(0, 2))
+            if canonical and (k + w - 1) % 2 == 0:
+                w = w + 1 if w < 127 else w - 1
+            pr = oracle.make_params(k, w, canonical=canonical)
+            pos, sk = oracle.run(packed, 1, n, pr, "stream", want_sk=True)
+            if len(pos) < 2:
+                continue
+            dp = np.diff(pos.astype(np.int64))
+            ds = np.diff(sk.astype(np.int64))
+            assert dp.max() <= w and dp.min() >= -(max(w, 2) - 2), (k, w, canonical, dp.min(), dp.max())
+            assert ds.min() >= 1 and ds.max() <= w, (k, w, canonical, ds.min(), ds.max())
+            saw_backward |= bool((dp < 0).any())
+    assert saw_backward  # the tie-heavy inputs do exercise the negative range
