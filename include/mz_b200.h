@@ -98,6 +98,11 @@ int mz_params_mulhash(mz_params* p, uint32_t k, uint32_t w, uint32_t mode, uint3
  * src/minimizers.rs:69-71). */
 int mz_params_set_nthash(mz_params* p, uint32_t hash_canonical);
 int mz_params_set_mulhash(mz_params* p, uint32_t hash_canonical);
+/* Any other table hasher (seeded hashers: `H::new_with_seed(k, seed)`, src/lib.rs:157,
+ * src/test.rs:287 -- seq-hash derives per-base tables from the seed; the Rust shim reads them out
+ * of the hasher object and passes them here). */
+int mz_params_set_tables(mz_params* p, const uint32_t f[4], const uint32_t c[4], uint32_t rot,
+                         uint32_t hash_canonical);
 /* Same checks the reference asserts on (see the error codes). */
 int mz_params_validate(const mz_params* p, uint64_t n_bp);
 
@@ -194,6 +199,40 @@ int mz_pack_ascii_n(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* packed_
 int mz_run_ascii_skip_ambiguous(mz_ctx* ctx, const mz_params* p, const char* ascii, uint64_t n, mz_out* out);
 
 int mz_last_timing(const mz_ctx* ctx, mz_timing* t);
+
+/*
+ * mz_values -- Output::values_u64 / values_u128 / pos_and_values_* (src/lib.rs:584-629), the
+ * reference's LAZY value iterators: the k-mer (minimizers) or l-mer (syncmers) at each of `n_pos`
+ * positions of the sequence, canonical builders return min(kmer, revcomp).  `pos` may be any
+ * positions (the reference iterates the caller's whole Vec, including entries of earlier runs);
+ * a position whose k-mer runs past the sequence gives MZ_ERR_BAD_ARG (read_kmer asserts).
+ * val_out: n_pos u64 (value_bits 64) or 2*n_pos u64 as (lo, hi) (value_bits 128).
+ * The shims run positions-only by default and call this when values are asked for; the sequence
+ * of the last single-launch mz_run on this context is still resident on the device and is not
+ * uploaded again (same `packed`, bp_offset, n_bp -- the caller must not have modified it, which
+ * the reference's `Output<'o, 's>` borrow guarantees).  Callers that always want values set
+ * mz_params.value_bits in mz_run instead (fused into the same kernel).
+ */
+int mz_values(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset, uint64_t n_bp,
+              const uint32_t* pos, uint64_t n_pos, uint32_t value_bits, uint64_t* val_out);
+
+/*
+ * mz_pcie_probe -- measured host <-> device copy rate of the context's devices, all of them at
+ * the same time (pinned host memory, `reps` copies of `bytes_per_device` per device and
+ * direction).  This is the ceiling of every end-to-end number of mz_run / mz_run_batch: one PCIe
+ * link per device, host memory and root complex shared.  GB/s, summed over the devices.
+ * The reference has no counterpart (it never leaves the host); bench.py reports it as
+ * e2e.pcie_peak_gbs.
+ */
+typedef struct mz_pcie_result {
+    double h2d_gbs;       /* host -> device alone                                                */
+    double d2h_gbs;       /* device -> host alone                                                */
+    double bidir_h2d_gbs; /* both directions at once: host -> device share                       */
+    double bidir_d2h_gbs; /*                          device -> host share                       */
+    uint32_t n_devices;
+    uint32_t reserved;
+} mz_pcie_result;
+int mz_pcie_probe(mz_ctx* ctx, uint64_t bytes_per_device, uint32_t reps, mz_pcie_result* res);
 
 #ifdef __cplusplus
 }

@@ -501,6 +501,133 @@ uint64_t mzo_run_mt(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_p
 }
 
 /* ------------------------------------------------------------------------------------------
+ * Batched short reads: the reference has no batch entry point, callers loop
+ *   for s in &seqs { v.clear(); builder.run(s, &mut v) }      (bench/src/bin/paper.rs:98-105,
+ * examples/bench.rs:63-89).  This is that loop over reads laid out at a fixed byte stride, every
+ * read a stand-alone sequence (positions relative to the read), results as CSR.  One scratch
+ * ring per thread, reused for every read (the reference keeps its scratch thread_local,
+ * src/lib.rs:217-219); threads take contiguous read ranges (rayon-over-reads analogue) and write
+ * straight into disjoint slices of the caller's arrays, closed up afterwards.
+ * ---------------------------------------------------------------------------------------- */
+typedef struct {
+    const uint8_t* packed;
+    uint64_t stride_bytes, r0, r1;
+    uint32_t read_len;
+    const mzo_params* p;
+    uint64_t* offsets; /* offsets[r + 1] = entries of read r (turned into a prefix sum later) */
+    uint32_t *pos, *sk;
+    uint64_t* val;
+    uint64_t cap, count;
+    int fail;
+} rd_job;
+
+static void stream_reset(stream_t* s, uint64_t off) {
+    s->off = off;
+    s->fw = s->rc = 0;
+    s->tg = -(int64_t)s->l;
+    for (uint32_t i = 0; i < s->w; i++) s->ringl[i] = ~0ull, s->ringr[i] = 0;
+    s->ridx = 0;
+    s->prel = ~0ull;
+    s->prer = 0;
+}
+
+static void* rd_worker(void* arg) {
+    rd_job* j = (rd_job*)arg;
+    const mzo_params* p = j->p;
+    const uint32_t l = p->k + p->w - 1, n = j->read_len;
+    const uint32_t len = p->mode == MZO_MINIMIZER ? p->k : l;
+    stream_t s;
+    j->count = 0;
+    if (stream_init(&s, j->packed, 0, p)) {
+        j->fail = 1;
+        return NULL;
+    }
+    uint64_t m = 0;
+    for (uint64_t r = j->r0; r < j->r1; r++) {
+        const uint64_t m0 = m;
+        if (n >= l) {
+            stream_reset(&s, r * j->stride_bytes * 4);
+            uint64_t sel, prev = ~0ull;
+            for (uint64_t t = 0; t < n; t++) {
+                if (!stream_step(&s, 0, t, &sel)) continue;
+                const uint64_t w0 = t + 1 - l;
+                int emit;
+                uint32_t v;
+                if (p->mode == MZO_MINIMIZER) emit = (w0 == 0 || sel != prev), prev = sel, v = (uint32_t)sel;
+                else if (p->mode == MZO_CLOSED_SYNCMER) emit = (sel == w0 || sel == w0 + p->w - 1), v = (uint32_t)w0;
+                else emit = (sel == w0 + p->w / 2), v = (uint32_t)w0;
+                if (emit) {
+                    if (m >= j->cap) {
+                        j->fail = 1;
+                        stream_free(&s);
+                        return NULL;
+                    }
+                    j->pos[m] = v;
+                    if (j->sk) j->sk[m] = (uint32_t)w0;
+                    m++;
+                }
+            }
+            if (j->val)
+                mzo_values_u64(j->packed, r * j->stride_bytes * 4, len, (int)p->strand_tiebreak, j->pos + m0,
+                               m - m0, j->val + m0);
+        }
+        j->offsets[r + 1] = m - m0;
+    }
+    stream_free(&s);
+    j->count = m;
+    return NULL;
+}
+
+uint64_t mzo_run_reads(const uint8_t* packed, uint64_t n_reads, uint64_t stride_bytes, uint32_t read_len,
+                       const mzo_params* p, int threads, uint64_t* offsets_out, uint32_t* pos_out,
+                       uint32_t* sk_out, uint64_t* val_out, uint64_t cap) {
+    if (!params_ok(p)) return (uint64_t)-1;
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n_reads) threads = n_reads ? (int)n_reads : 1;
+    rd_job* jobs = (rd_job*)calloc((size_t)threads, sizeof(rd_job));
+    pthread_t* th = (pthread_t*)calloc((size_t)threads, sizeof(pthread_t));
+    const uint64_t per = (n_reads + (uint64_t)threads - 1) / (uint64_t)threads;
+    const uint64_t slice = cap / (uint64_t)threads;
+    offsets_out[0] = 0;
+    for (int t = 0; t < threads; t++) {
+        rd_job* j = &jobs[t];
+        j->packed = packed, j->stride_bytes = stride_bytes, j->read_len = read_len, j->p = p;
+        j->r0 = per * (uint64_t)t < n_reads ? per * (uint64_t)t : n_reads;
+        j->r1 = j->r0 + per < n_reads ? j->r0 + per : n_reads;
+        j->offsets = offsets_out;
+        j->pos = pos_out + slice * (uint64_t)t;
+        j->sk = sk_out ? sk_out + slice * (uint64_t)t : NULL;
+        j->val = val_out ? val_out + slice * (uint64_t)t : NULL;
+        j->cap = slice;
+    }
+    if (threads == 1) rd_worker(&jobs[0]);
+    else {
+        for (int t = 0; t < threads; t++) pthread_create(&th[t], NULL, rd_worker, &jobs[t]);
+        for (int t = 0; t < threads; t++) pthread_join(th[t], NULL);
+    }
+    uint64_t m = 0;
+    int ok = 1;
+    for (int t = 0; t < threads; t++) {
+        rd_job* j = &jobs[t];
+        if (j->fail) {
+            ok = 0;
+            break;
+        }
+        if (t && j->count) { /* close the gap between the thread slices */
+            memmove(pos_out + m, j->pos, sizeof(uint32_t) * j->count);
+            if (sk_out) memmove(sk_out + m, j->sk, sizeof(uint32_t) * j->count);
+            if (val_out) memmove(val_out + m, j->val, sizeof(uint64_t) * j->count);
+        }
+        m += j->count;
+    }
+    if (ok)
+        for (uint64_t r = 0; r < n_reads; r++) offsets_out[r + 1] += offsets_out[r];
+    free(jobs);
+    free(th);
+    return ok ? m : (uint64_t)-1;
+}
+
+/* ------------------------------------------------------------------------------------------
  * synthetic input
  * ---------------------------------------------------------------------------------------- */
 static inline uint64_t splitmix64(uint64_t x) {

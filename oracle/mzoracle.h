@@ -108,6 +108,16 @@ uint64_t mzo_run_mt(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_p
                     int threads, uint32_t* pos_out, uint32_t* sk_out, uint64_t* val_out,
                     uint64_t cap);
 
+/* Batched short reads = the caller loop `for s in &seqs { v.clear(); builder.run(s, &mut v) }`
+ * (bench/src/bin/paper.rs:98-105, examples/bench.rs:63-89) over reads of `read_len` bases laid
+ * out every `stride_bytes` bytes; CSR result (offsets_out: n_reads + 1 entries), positions
+ * relative to the read.  `threads` workers take contiguous read ranges.  val_out (may be NULL):
+ * u64 values, k <= 32 (minimizers) / l <= 32 (syncmers).  Returns the entry count,
+ * (uint64_t)-1 on bad parameters or when cap / threads entries do not hold a thread's share. */
+uint64_t mzo_run_reads(const uint8_t* packed, uint64_t n_reads, uint64_t stride_bytes, uint32_t read_len,
+                       const mzo_params* p, int threads, uint64_t* offsets_out, uint32_t* pos_out,
+                       uint32_t* sk_out, uint64_t* val_out, uint64_t cap);
+
 /* k-mer values for positions (src/lib.rs:598-629). len <= 32 for u64, <= 64 for u128
  * (lo,hi pairs). */
 void mzo_values_u64(const uint8_t* packed, uint64_t off, uint32_t len, int canonical,

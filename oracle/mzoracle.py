@@ -80,6 +80,9 @@ def lib():
         L.mzo_run_skip_ambiguous.argtypes = [u8p, C.c_uint64, C.c_uint64, u8p, C.c_uint64,
                                              C.POINTER(Params), C.c_int, u32p]
         L.mzo_run_skip_ambiguous.restype = C.c_uint64
+        L.mzo_run_reads.argtypes = [u8p, C.c_uint64, C.c_uint64, C.c_uint32, C.POINTER(Params), C.c_int,
+                                    u64p, u32p, u32p, u64p, C.c_uint64]
+        L.mzo_run_reads.restype = C.c_uint64
         L.mzb_run_mt.argtypes = L.mzo_run_mt.argtypes
         L.mzb_run_mt.restype = C.c_uint64
         L.mzb_have_avx2.restype = C.c_int
@@ -102,6 +105,15 @@ def make_hasher(kind: str = "nt", canonical: bool = True) -> Hasher:
         lib().mzo_hasher_mul(C.byref(h), int(canonical))
     else:
         raise ValueError(kind)
+    return h
+
+
+def make_hasher_tables(f, c, rot: int, canonical: bool) -> Hasher:
+    """Any table hasher (seeded hashers cross the product's ABI the same way)."""
+    h = Hasher()
+    for b in range(4):
+        h.f[b], h.c[b] = int(f[b]) & 0xffffffff, int(c[b]) & 0xffffffff
+    h.rot, h.canonical = int(rot), int(canonical)
     return h
 
 
@@ -200,6 +212,26 @@ def run_mt(packed, off, n, params: Params, threads: int, want_sk=False, want_val
     if m == ERR:
         raise ValueError("oracle: run_mt failed (parameters or capacity)")
     return pos[:m], (sk[:m] if want_sk else None), (val[:m] if want_val else None)
+
+
+def run_reads(packed, n_reads, stride_bytes, read_len, params: Params, threads: int = 1,
+              want_sk=False, want_val=False, bufs=None):
+    """The per-read caller loop (bench/src/bin/paper.rs:98-105) over fixed-stride reads: CSR
+    (offsets, pos, sk, val).  ``bufs`` = pre-allocated (offsets, pos, sk, val) arrays (timed runs
+    allocate and touch them outside the timed region)."""
+    l = params.k + params.w - 1
+    nwin = max(0, read_len - l + 1)
+    if bufs is None:
+        cap = max(nwin * n_reads, 1)
+        bufs = (np.zeros(n_reads + 1, dtype=np.uint64), np.zeros(cap, dtype=np.uint32),
+                np.zeros(cap, dtype=np.uint32) if want_sk else None,
+                np.zeros(cap, dtype=np.uint64) if want_val else None)
+    offs, pos, sk, val = bufs
+    m = lib().mzo_run_reads(_ptr(packed), n_reads, stride_bytes, read_len, C.byref(params), threads,
+                            _ptr(offs), _ptr(pos), _ptr(sk), _ptr(val), len(pos))
+    if m == ERR:
+        raise ValueError("oracle: run_reads failed (parameters or capacity)")
+    return offs, pos[:m], (sk[:m] if sk is not None else None), (val[:m] if val is not None else None)
 
 
 def baseline_run_mt(packed, off, n, params: Params, threads: int, want_sk=False, want_val=False,

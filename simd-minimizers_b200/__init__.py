@@ -224,13 +224,38 @@ class _TableHasher:
     def new(cls, k: int, canonical: bool = True):
         return cls(k, canonical)
 
-    def k(self) -> int:
-        return self._k
-
     def is_canonical(self) -> bool:
         return self._canonical
 
+    @classmethod
+    def new_with_seed(cls, k: int, seed: int, canonical: bool = True):
+        """``H::new_with_seed(k, seed)`` (src/lib.rs:157, src/test.rs:287).  seq-hash 0.2.0 derives
+        the per-base tables from the seed inside the un-vendored crate, so the arithmetic cannot
+        be restated here; the Rust shim reads the tables out of the hasher object.  Pass them with
+        ``from_tables`` instead."""
+        raise NotImplementedError(
+            "seeded tables live in seq-hash (not in the reference tree): use "
+            f"{cls.__name__}.from_tables(k, f, c, rot, canonical) with the tables of the seeded hasher")
+
+    @classmethod
+    def from_tables(cls, k: int, f, c, rot: int = 7, canonical: bool = True):
+        """Any table hasher (seeded NtHasher / MulHasher): fw = XOR rotl(f[b], rot*(k-1-j)),
+        rc = XOR rotl(c[b], rot*j), tables indexed by packed code A=0 C=1 T=2 G=3."""
+        h = cls(k, canonical)
+        h._tables = ([int(x) & 0xffffffff for x in f], [int(x) & 0xffffffff for x in c], int(rot))
+        assert len(h._tables[0]) == 4 and len(h._tables[1]) == 4
+        return h
+
+    def k(self) -> int:
+        return self._k
+
     def _apply(self, p: MzParams):
+        t = getattr(self, "_tables", None)
+        if t is not None:
+            f, c, rot = t
+            _check(_ffi.lib().mz_params_set_tables(C.byref(p), (C.c_uint32 * 4)(*f), (C.c_uint32 * 4)(*c),
+                                                   rot, int(self._canonical)))
+            return
         _check(getattr(_ffi.lib(), self._setter)(C.byref(p), int(self._canonical)))
 
 
@@ -239,6 +264,9 @@ class NtHasher(_TableHasher):
 
 
 class MulHasher(_TableHasher):
+    """seq-hash MulHasher.  The tables behind mz_params_set_mulhash are a restatement that no
+    vector of the reference pins: GPU == oracle is tested, reference parity is
+    open until tests/golden/reference_dump.json is generated with the crate."""
     _setter = "mz_params_set_mulhash"
 
 
@@ -340,25 +368,30 @@ def _as_vec(v):
 # Builder / Output  (src/lib.rs:225-630)
 # ------------------------------------------------------------------------------------------
 class Output:
-    """src/lib.rs:232-237, 579-630.  ``len`` is k for minimizers, k+w-1 for syncmers."""
+    """src/lib.rs:232-237, 579-630.  ``len`` is k for minimizers, k+w-1 for syncmers.  Values are
+    lazy, as in the reference: ``run`` moves positions only, ``values_*`` computes the k-mers of
+    *all* of ``min_pos`` on the device (mz_values; the sequence of the run is still resident there)."""
 
-    def __init__(self, builder: "Builder", seq: PackedSeq, min_pos: U32Vec, start: int, vals64,
-                 src=None, skip: bool = False):
+    def __init__(self, builder: "Builder", seq, min_pos: U32Vec):
         self.len = builder.k if builder.syncmer == 0 else builder.k + builder.w - 1
-        self._b, self.seq, self.min_pos, self._start, self._vals64 = builder, seq, min_pos, start, vals64
-        self._src, self._skip = (src if src is not None else seq), skip
+        self._b, self.seq, self.min_pos = builder, seq, min_pos
 
     def _values(self, bits: int) -> np.ndarray:
         if self.len > bits // 2:
             raise AssertionError(_ffi.lib().mz_strerror(7).decode())
-        # Values cover *all* of min_pos (the reference iterates the whole Vec, src/lib.rs:599).
-        if bits == 64 and self._vals64 is not None and self._start == 0:
-            return self._vals64
-        if self._start != 0:
-            raise NotImplementedError("values of positions appended by an earlier run: call "
-                                      "U32Vec.clear() between runs")
-        _, _, vals = self._b._execute(self._src, value_bits=bits, skip=self._skip)
-        return vals
+        seq = self.seq
+        if isinstance(seq, AsciiSeq):  # packed on the device, values read the packed form
+            seq = seq.pack(self._b._ctx).as_slice()
+        elif isinstance(seq, PackedNSeq):
+            seq = seq.seq
+        p = self._b._params(0)
+        ctx = self._b._ctx or default_context()
+        pos = np.ascontiguousarray(self.min_pos.array, dtype=np.uint32)
+        vw = bits // 64
+        val = np.empty(max(pos.size, 1) * vw, dtype=np.uint64)
+        _check(_ffi.lib().mz_values(ctx.handle, C.byref(p), seq.data.ctypes.data, seq.offset, seq.len,
+                                    pos.ctypes.data, pos.size, bits, val.ctypes.data))
+        return val[:pos.size] if vw == 1 else val[:2 * pos.size].reshape(pos.size, 2)
 
     def values_u64(self):
         return self._values(64)
@@ -457,27 +490,50 @@ class Builder:
         return pos[:m], (sk[:m] if sk is not None else None), vals
 
     def run(self, seq, min_pos: U32Vec) -> Output:
-        """Append positions to ``min_pos`` (and super-k-mer starts to the sk vector)."""
+        """Append positions to ``min_pos`` (and super-k-mer starts to the sk vector).  Positions
+        only cross the bus; ``Output.values_*`` are lazy (src/lib.rs:598-629)."""
         min_pos = _as_vec(min_pos)
-        length = self.k if self.syncmer == 0 else self.k + self.w - 1
-        bits = 64 if length <= 32 else 0
-        pos, sk, vals = self._execute(seq, bits)
-        start = len(min_pos)
+        pos, sk, _ = self._execute(seq, 0)
         # SIMD-collector quirk (src/collect.rs:257,267): the first new element is dropped when
         # it equals the caller's current last element.  Syncmers are appended verbatim
         # (src/syncmers.rs:167-169).
-        if self.syncmer == 0 and start and pos.size and int(pos[0]) == min_pos.last():
+        if self.syncmer == 0 and len(min_pos) and pos.size and int(pos[0]) == min_pos.last():
             pos, sk = pos[1:], (sk[1:] if sk is not None else None)
-            vals = vals[1:] if vals is not None else None
         min_pos._extend(pos)
         if self._sk_pos is not None:
             self._sk_pos._extend(sk)
-        return Output(self, seq.as_slice(), min_pos, start, vals)
+        return Output(self, seq.as_slice(), min_pos)
 
     def run_once(self, seq) -> np.ndarray:
         v = U32Vec()
         self.run(seq, v)
         return v.array
+
+    def run_scalar(self, seq, min_pos: U32Vec) -> Output:
+        """``run_scalar`` (src/lib.rs:372-378, 508-533): the same result through the reference's
+        scalar collectors, which OVERWRITE the vectors from index 0 instead of appending
+        (src/collect.rs:15-76, src/syncmers.rs:19-48).  Same device path here (the reference
+        asserts scalar == SIMD, src/test.rs:53-84)."""
+        min_pos = _as_vec(min_pos)
+        pos, sk, _ = self._execute(seq, 0)
+        min_pos.clear()
+        min_pos._extend(pos)
+        if self._sk_pos is not None and seq.as_slice().len >= self.k + self.w - 1:
+            # an empty window stream leaves the index vector untouched (src/collect.rs:45-48)
+            self._sk_pos.clear()
+            self._sk_pos._extend(sk)
+        return Output(self, seq.as_slice(), min_pos)
+
+    def run_scalar_once(self, seq) -> np.ndarray:
+        v = U32Vec()
+        self.run_scalar(seq, v)
+        return v.array
+
+    def run_with_values(self, seq, value_bits: int = 64, skip_ambiguous: bool = False):
+        """Not in the reference: positions (+ super-k-mer starts) AND values in one fused launch
+        (mz_params.value_bits), for callers that always consume the values (bench.py's pos+vals
+        metric).  Returns (pos, sk, vals); u128 values come as an (n, 2) array of (lo, hi)."""
+        return self._execute(seq, value_bits, skip=skip_ambiguous)
 
     def run_skip_ambiguous_windows(self, nseq, min_pos: U32Vec) -> Output:
         """src/lib.rs:451-496: windows containing an ambiguous base produce nothing.  ``nseq`` is
@@ -488,16 +544,11 @@ class Builder:
         if not isinstance(nseq, (PackedNSeq, PackedNSeqVec, AsciiSeq)):
             raise TypeError("run_skip_ambiguous_windows takes a PackedNSeq")
         min_pos = _as_vec(min_pos)
-        length = self.k if self.syncmer == 0 else self.k + self.w - 1
-        pos, _, vals = self._execute(nseq, 64 if length <= 32 else 0, skip=True)
-        start = len(min_pos)
-        if self.syncmer == 0 and start and pos.size and int(pos[0]) == min_pos.last():
+        pos, _, _ = self._execute(nseq, 0, skip=True)
+        if self.syncmer == 0 and len(min_pos) and pos.size and int(pos[0]) == min_pos.last():
             pos = pos[1:]
-            vals = vals[1:] if vals is not None else None
         min_pos._extend(pos)
-        src = nseq.as_slice()
-        seq = src.seq if isinstance(src, PackedNSeq) else src
-        return Output(self, seq, min_pos, start, vals, src=src, skip=True)
+        return Output(self, nseq.as_slice(), min_pos)
 
     def run_skip_ambiguous_windows_once(self, nseq) -> np.ndarray:
         v = U32Vec()

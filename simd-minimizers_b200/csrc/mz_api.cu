@@ -107,8 +107,8 @@ unsigned host_threads() {
 }
 
 // memcpy split over a few host threads (a single thread cannot keep up with a Gen5 x16 link)
-void parallel_memcpy(void* dst, const void* src, size_t bytes) {
-    unsigned nt = host_threads();
+void parallel_memcpy(void* dst, const void* src, size_t bytes, unsigned max_threads = 0) {
+    unsigned nt = max_threads ? std::min(max_threads, host_threads()) : host_threads();
     if (bytes < (8u << 20)) nt = 1;
     if (nt == 1) {
         memcpy(dst, src, bytes);
@@ -134,7 +134,7 @@ struct DevState {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // H2D begin/end, kernel end, D2H end, D2H begin
     DevBuf<unsigned long long> scratch;  // [0]=count [1]=ticket|overflow [2..]=tile_state
     DevBuf<uint32_t> rows;               // fast kernel per-block record rows
     DevBuf<uint8_t> in;
@@ -162,6 +162,13 @@ struct mz_ctx {
     std::vector<DevState> devs;                 // slot 0 of every device
     std::vector<std::vector<DevState>> extra;   // slots 1..kSlots-1 of every device
     mz_timing timing{};
+    // The sequence the last single-launch mz_run left in devs[0].in (mz_values reuses it instead of
+    // uploading it again: Output::values_*() right after run()); cleared by every other use of the buffer.
+    struct Resident {
+        const uint8_t* packed = nullptr;
+        uint64_t bp_offset = 0, n_bp = 0, byte_lo = 0;
+        size_t nbytes = 0;
+    } resident;
     DevState& slot(size_t dev, int s) { return s == 0 ? devs[dev] : extra[dev][s - 1]; }
 };
 
@@ -348,7 +355,7 @@ cudaError_t init_devstate(DevState& d, int device) {
     d.device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
-    for (int j = 0; j < 4 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
+    for (int j = 0; j < 5 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable | cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&d.hs_dev, d.hs, 0);
     int v = 0;
@@ -435,11 +442,11 @@ __global__ void mz_delta_encode_kernel(const uint32_t* __restrict__ v, uint64_t 
 size_t delta_bytes(uint64_t n) {  // [deltas, padded to 4][bases]
     return (size_t)((n + 3) & ~uint64_t(3)) + (size_t)((n + kDeltaBlock - 1) / kDeltaBlock) * 4;
 }
-void delta_decode(const unsigned char* enc, uint64_t n, uint32_t* out) {
+void delta_decode(const unsigned char* enc, uint64_t n, uint32_t* out, unsigned max_threads = 0) {
     const int8_t* delta = reinterpret_cast<const int8_t*>(enc);
     const uint32_t* base = reinterpret_cast<const uint32_t*>(enc + ((n + 3) & ~uint64_t(3)));
     const uint64_t nblk = (n + kDeltaBlock - 1) / kDeltaBlock;
-    unsigned nt = host_threads();
+    unsigned nt = max_threads ? std::min(max_threads, host_threads()) : host_threads();
     if (nblk < 64) nt = 1;
     auto work = [=](uint64_t b0, uint64_t b1) {
         for (uint64_t b = b0; b < b1; b++) {
@@ -465,40 +472,83 @@ void delta_decode(const unsigned char* enc, uint64_t n, uint32_t* out) {
     for (auto& t : th) t.join();
 }
 
-// Single device, large input: windows are cut into chunks that flow through kSlots streams so
-// that the H2D copy of chunk c+2, the kernel of chunk c+1 and the D2H copy of chunk c overlap.
-// Chunks are seams like any other shard (one extra window on the left); outputs land in the
-// caller's arrays in order.
-int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64_t bp_offset,
+// Large inputs, any number of devices: windows are cut into chunks; chunk c runs on device
+// c % ndev in stream slot (c / ndev) % kSlots of that device, so that on every device the H2D copy
+// of one chunk, the kernel of the next and the D2H copy of an earlier one overlap, and all devices
+// (one PCIe link each) move data at the same time.  Chunks are seams like any other shard (one
+// extra window on the left); because they are dealt out in order, the output offset of chunk c
+// (the sum of the counts of all chunks before it) is known as soon as the kernels of chunks
+// 0..c have finished, whichever devices they ran on, and every D2H copy lands directly at its
+// final place in the caller's arrays: one ordered, globally indexed output, no second pass.
+int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* packed, uint64_t bp_offset,
                   uint64_t n_bp, const AmbSrc& am, mz_out* out) {
     const uint32_t l = p.k + p.w - 1;
     const uint64_t nwin = n_bp - l + 1;
     const uint32_t vw = p.value_bits / 64;
-    uint64_t chunk = std::max<uint64_t>(1ull << 25, (nwin + 23) / 24);
+    // >= 24 chunks, >= 6 per device, but never tiny ones (launch + copy latency)
+    uint64_t chunk = std::max<uint64_t>(ndev == 1 ? (1ull << 25) : (1ull << 22),
+                                        (nwin + std::max<uint64_t>(24, 6 * ndev) - 1) / std::max<uint64_t>(24, 6 * ndev));
     const char* env = getenv("MZ_CHUNK_WINDOWS");
     if (env) chunk = std::max<uint64_t>(1, strtoull(env, nullptr, 10));
     const uint64_t nchunks = (nwin + chunk - 1) / chunk;
+    const uint64_t ND = ndev;
     struct Job {
         uint64_t wb, we, cap, byte_lo, count = 0, out_off = 0, abyte_lo = 0;
         size_t nbytes, anbytes = 0;
         bool staged = false;
+        float decode_ms = 0;
     };
     // Pageable caller memory goes through pinned bounce buffers + multi-threaded memcpy; pinned
     // (mz_host_alloc / cudaHostRegister'ed) memory is used directly.
     const bool page_in = is_pageable(packed);
     const bool page_out = is_pageable(out->pos) || (p.want_sk && is_pageable(out->sk)) || (vw && is_pageable(out->val));
-    // positions (and super-k-mer starts) of plain minimizer runs cross PCIe delta-coded
-    const bool delta = p.mode == MZ_MODE_MINIMIZER && p.w <= 127 && !am.bits && !getenv("MZ_NO_POS_DELTA");
+    // positions (and super-k-mer starts) of plain minimizer runs cross PCIe delta-coded.  With
+    // several devices the links add up but the host cores that decode do not: the codec is used
+    // while the decode rate (MZ_DELTA_MAX_DEVICES, default 2) keeps up with the links.
+    static const uint64_t delta_max_dev = getenv("MZ_DELTA_MAX_DEVICES") ? strtoull(getenv("MZ_DELTA_MAX_DEVICES"), nullptr, 10) : 2;
+    const bool delta = p.mode == MZ_MODE_MINIMIZER && p.w <= 127 && !am.bits && !getenv("MZ_NO_POS_DELTA") && ND <= delta_max_dev;
+    // host threads per decode / copy-out job: the jobs of all devices run side by side
+    const unsigned job_threads = std::max(2u, host_threads() / (unsigned)std::min<uint64_t>(ND, 4));
     std::vector<Job> jobs(nchunks);
     uint64_t total = 0;
     bool too_small = false;
     int rc;
     double dbg_sync_ms = 0;  // MZ_DEBUG_PIPE: time the calling thread waits for kernels
-    CK(cudaSetDevice(ctx->devs[0].device));
+    const auto t_start = std::chrono::steady_clock::now();
+    std::vector<float> dev_h2d(ND, 0.f), dev_ker(ND, 0.f), dev_d2h(ND, 0.f);
+
+    // D2H time of the chunk that used a slot last (its copies have completed when this is called)
+    std::vector<char> d2h_pending(ndev * kSlots, 0);
+    auto collect_d2h = [&](size_t di, int sl) {
+        if (!d2h_pending[di * kSlots + sl]) return;
+        d2h_pending[di * kSlots + sl] = 0;
+        DevState& d = ctx->slot(di, sl);
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, d.ev[4], d.ev[3]) == cudaSuccess) dev_d2h[di] += ms;
+        else cudaGetLastError();
+    };
+    auto dev_of = [&](uint64_t c) { return (size_t)(c % ND); };
+    auto slot_of = [&](uint64_t c) { return (int)((c / ND) % kSlots); };
+    // error paths return early: no stream may still be writing the caller's arrays, and no
+    // joinable thread may be destroyed (declared first, so it runs after the helpers are joined)
+    struct SyncAll {
+        mz_ctx* ctx;
+        size_t ndev;
+        ~SyncAll() {
+            for (size_t i = 0; i < ndev; i++)
+                for (int sl = 0; sl < kSlots; sl++) {
+                    DevState& d = ctx->slot(i, sl);
+                    if (cudaSetDevice(d.device) == cudaSuccess) cudaStreamSynchronize(d.stream);
+                }
+            cudaGetLastError();
+            cudaSetDevice(ctx->devs[0].device);
+        }
+    } sync_all{ctx, ndev};
 
     auto issue = [&](uint64_t c) -> int {
-        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
         Job& j = jobs[c];
+        CK(cudaSetDevice(d.device));
         j.wb = c * chunk;
         j.we = std::min<uint64_t>(j.wb + chunk, nwin);
         j.cap = estimate_capacity(p, j.we - j.wb);
@@ -529,68 +579,74 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         return MZ_OK;
     };
     // D2H of chunk c enqueued -> a helper thread waits for it and writes the caller's arrays (delta
-    // decode / copy out of the bounce buffers), so the calling thread keeps the pipeline fed
-    std::thread helper[kSlots];
-    int helper_rc[kSlots] = {};
-    struct JoinAll {  // error paths return early: never destroy a joinable thread
-        std::thread* h;
+    // decode / copy out of the bounce buffers), so the calling thread keeps the pipelines fed
+    const size_t nhelp = ndev * kSlots;
+    std::vector<std::thread> helper(nhelp);
+    std::vector<int> helper_rc(nhelp, 0);
+    struct JoinAll {
+        std::vector<std::thread>& h;
         ~JoinAll() {
-            for (int i = 0; i < kSlots; i++)
-                if (h[i].joinable()) h[i].join();
+            for (auto& t : h)
+                if (t.joinable()) t.join();
         }
     } join_all{helper};
-    auto join_helper = [&](int sl) -> int {
-        if (helper[sl].joinable()) helper[sl].join();
-        const int r = helper_rc[sl];
-        helper_rc[sl] = 0;
+    auto join_helper = [&](size_t hi) -> int {
+        if (helper[hi].joinable()) helper[hi].join();
+        const int r = helper_rc[hi];
+        helper_rc[hi] = 0;
         return r;
     };
     auto finish = [&](uint64_t c) -> int {
-        const int sl = (int)(c % kSlots);
-        DevState& d = ctx->slot(0, sl);
+        const size_t hi = dev_of(c) * kSlots + slot_of(c);
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
         Job& j = jobs[c];
         if (!(j.staged || delta) || !j.count || too_small) return MZ_OK;
-        int r = join_helper(sl);
+        int r = join_helper(hi);
         if (r) return r;
-        const int device = ctx->devs[0].device;
         const bool want_sk = p.want_sk != 0;
-        auto work = [&d, &j, &helper_rc, sl, out, vw, delta, want_sk, device]() {
-            if (cudaSetDevice(device) != cudaSuccess || cudaEventSynchronize(d.ev[3]) != cudaSuccess) {
-                helper_rc[sl] = MZ_ERR_CUDA;
+        int* const hrc = &helper_rc[hi];
+        auto work = [&d, &j, hrc, out, vw, delta, want_sk, job_threads]() {
+            if (cudaSetDevice(d.device) != cudaSuccess || cudaEventSynchronize(d.ev[3]) != cudaSuccess) {
+                *hrc = MZ_ERR_CUDA;
                 return;
             }
+            const auto t0 = std::chrono::steady_clock::now();
             if (delta) {
-                delta_decode(d.st_delta.p, j.count, out->pos + j.out_off);
-                if (want_sk) delta_decode(d.st_delta.p + delta_bytes(j.count), j.count, out->sk + j.out_off);
+                delta_decode(d.st_delta.p, j.count, out->pos + j.out_off, job_threads);
+                if (want_sk) delta_decode(d.st_delta.p + delta_bytes(j.count), j.count, out->sk + j.out_off, job_threads);
             } else {
-                parallel_memcpy(out->pos + j.out_off, d.st_pos.p, j.count * 4);
-                if (want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4);
+                parallel_memcpy(out->pos + j.out_off, d.st_pos.p, j.count * 4, job_threads);
+                if (want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4, job_threads);
             }
-            if (vw && j.staged) parallel_memcpy(out->val + j.out_off * vw, d.st_val.p, j.count * 8 * vw);
+            if (vw && j.staged) parallel_memcpy(out->val + j.out_off * vw, d.st_val.p, j.count * 8 * vw, job_threads);
+            j.decode_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         };
         try {
-            helper[sl] = std::thread(work);
+            helper[hi] = std::thread(work);
         } catch (...) {  // no thread to be had: do it here (nothing may unwind across the C ABI)
             work();
-            r = helper_rc[sl];
-            helper_rc[sl] = 0;
+            r = helper_rc[hi];
+            helper_rc[hi] = 0;
             if (r) return r;
         }
         return MZ_OK;
     };
     auto retire = [&](uint64_t c) -> int {
-        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        const size_t di = dev_of(c);
+        DevState& d = ctx->slot(di, slot_of(c));
         Job& j = jobs[c];
+        CK(cudaSetDevice(d.device));
         {
             const auto ts0 = std::chrono::steady_clock::now();
-            CK(cudaStreamSynchronize(d.stream));
+            CK(cudaEventSynchronize(d.ev[2]));
             dbg_sync_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
         }
         float h2d = 0, ker = 0;
         cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
         cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
-        ctx->timing.h2d_ms += h2d;
-        ctx->timing.kernel_ms += ker;
+        dev_h2d[di] += h2d;
+        dev_ker[di] += ker;
+        collect_d2h(di, slot_of(c));  // the slot's previous chunk (stream order: it is out)
         uint64_t count = d.hs->count;
         if (d.hs->overflow) {  // capacity estimate too small: redo this chunk with the exact size
             int r;
@@ -615,7 +671,7 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         j.out_off = total;
         if (!too_small && count) {
             // the slot's bounce buffers are about to be overwritten: its previous chunk must be out
-            if (int r = join_helper((int)(c % kSlots))) return r;
+            if (int r = join_helper(di * kSlots + slot_of(c))) return r;
             uint32_t *hpos = out->pos + total, *hsk = p.want_sk ? out->sk + total : nullptr;
             uint64_t* hval = vw ? out->val + total * vw : nullptr;
             if (page_out) {
@@ -628,6 +684,8 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
                 hval = reinterpret_cast<uint64_t*>(d.st_val.p);
                 j.staged = true;
             }
+            CK(cudaEventRecord(d.ev[4], d.stream));
+            d2h_pending[di * kSlots + slot_of(c)] = 1;
             if (delta) {
                 int r;
                 const size_t nb = delta_bytes(count), narr = p.want_sk ? 2 : 1;
@@ -653,32 +711,64 @@ int run_pipelined(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64
         total += count;
         return MZ_OK;
     };
-    if (!page_out && !delta) {
-        for (uint64_t c = 0; c < nchunks; c++) {
-            if ((rc = issue(c))) return rc;
-            if (c + 1 >= (uint64_t)kSlots && (rc = retire(c + 1 - kSlots))) return rc;
-        }
-        for (uint64_t c = nchunks >= (uint64_t)kSlots ? nchunks - (kSlots - 1) : 0; c < nchunks; c++)
-            if ((rc = retire(c))) return rc;
-    } else {
-        // stages in flight: H2D + kernel of chunks c, c-1 | D2H(c-2) | decode / copy-out(c-3) on a
-        // helper thread.  Issuing two chunks ahead keeps the calling thread from waiting for an
-        // H2D copy that it has only just enqueued.
-        constexpr uint64_t R = kSlots - 2, F = kSlots - 1;
-        for (uint64_t c = 0; c < nchunks + F; c++) {
-            if (c < nchunks && (rc = issue(c))) return rc;
-            if (c >= R && c - R < nchunks && (rc = retire(c - R))) return rc;
-            if (c >= F && (rc = finish(c - F))) return rc;
-        }
+    // chunks issued ahead of the one being retired: two per device (H2D + kernel of c, c - ndev
+    // in flight while the D2H of c - 2 ndev runs), three without the helper stage
+    const bool helpers = page_out || delta;
+    const uint64_t R = (helpers ? kSlots - 2 : kSlots - 1) * ND, F = R + ND;
+    for (uint64_t c = 0; c < nchunks + F; c++) {
+        if (c < nchunks && (rc = issue(c))) return rc;
+        if (c >= R && c - R < nchunks && (rc = retire(c - R))) return rc;
+        if (helpers && c >= F && c - F < nchunks && (rc = finish(c - F))) return rc;
     }
-    for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(ctx->slot(0, sl).stream));
-    for (int sl = 0; sl < kSlots; sl++)
-        if (int r = join_helper(sl)) return r;
-    if (getenv("MZ_DEBUG_PIPE"))
-        fprintf(stderr, "[mz pipeline] chunks %llu delta %d: host waited %.1f ms for kernels\n",
-                (unsigned long long)nchunks, (int)delta, dbg_sync_ms);
+    for (size_t i = 0; i < ndev; i++)
+        for (int sl = 0; sl < kSlots; sl++) {
+            DevState& d = ctx->slot(i, sl);
+            CK(cudaSetDevice(d.device));
+            CK(cudaStreamSynchronize(d.stream));
+        }
+    for (size_t hi = 0; hi < nhelp; hi++)
+        if (int r = join_helper(hi)) return r;
+    for (size_t hi = 0; hi < nhelp; hi++) collect_d2h(hi / kSlots, (int)(hi % kSlots));
+    for (size_t i = 0; i < ndev; i++) {  // per-phase times: the busiest device
+        ctx->timing.h2d_ms = std::max(ctx->timing.h2d_ms, dev_h2d[i]);
+        ctx->timing.kernel_ms = std::max(ctx->timing.kernel_ms, dev_ker[i]);
+        ctx->timing.d2h_ms = std::max(ctx->timing.d2h_ms, dev_d2h[i]);
+    }
+    CK(cudaSetDevice(ctx->devs[0].device));
+    if (getenv("MZ_DEBUG_PIPE")) {
+        const double wall = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count();
+        double dec = 0;
+        for (const Job& j : jobs) dec += j.decode_ms;
+        fprintf(stderr, "[mz pipeline] devices %zu chunks %llu (%llu windows each) delta %d: wall %.1f ms, calling thread "
+                        "waited %.1f ms for kernels, helper threads %.1f ms (%u threads per job)\n",
+                ndev, (unsigned long long)nchunks, (unsigned long long)chunk, (int)delta, wall, dbg_sync_ms, dec, job_threads);
+        for (size_t i = 0; i < ndev; i++)
+            fprintf(stderr, "[mz pipeline]   device %d: h2d %.2f ms, kernels %.2f ms, d2h %.2f ms (sums over its chunks)\n",
+                    ctx->devs[i].device, dev_h2d[i], dev_ker[i], dev_d2h[i]);
+    }
     out->count = total;
     return too_small ? MZ_ERR_CAPACITY : MZ_OK;
+}
+
+// Output::values_u64 / values_u128 (src/lib.rs:598-629): one thread per position.
+__global__ void mz_values_kernel(mz::KArgs a, const uint32_t* __restrict__ pos, uint64_t n, uint64_t n_bp,
+                                 uint64_t* __restrict__ val, uint32_t* __restrict__ bad) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint64_t p = pos[i];
+    if (p + a.val_len > n_bp) {  // the reference's read_kmer asserts on this
+        *bad = 1u;
+        return;
+    }
+    const uint64_t bit = (uint64_t)((int64_t)(2 * p) + a.bitbias);
+    if (a.value_bits == 64) {
+        __stcs(reinterpret_cast<unsigned long long*>(val) + i,
+               (unsigned long long)mz::kmer_value_u64(a, bit, a.val_len, a.val_canonical != 0));
+    } else {
+        uint64_t lo, hi;
+        mz::kmer_value_u128(a, bit, a.val_len, a.val_canonical != 0, lo, hi);
+        reinterpret_cast<ulonglong2*>(val)[i] = make_ulonglong2(lo, hi);
+    }
 }
 
 // ASCII -> 2-bit packing, (c >> 1) & 3 per character; one thread per 16 characters.
@@ -925,6 +1015,136 @@ void mz_host_free(void* p) {
     if (p) cudaFreeHost(p);
 }
 
+int mz_params_set_tables(mz_params* p, const uint32_t f[4], const uint32_t c[4], uint32_t rot,
+                         uint32_t hash_canonical) {
+    if (!p || !f || !c || rot > 31) return MZ_ERR_BAD_ARG;
+    for (int b = 0; b < 4; b++) p->f[b] = f[b], p->c[b] = c[b];
+    p->rot = rot;
+    p->hash_canonical = hash_canonical ? 1u : 0u;
+    return MZ_OK;
+}
+
+int mz_values(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset, uint64_t n_bp,
+              const uint32_t* pos, uint64_t n_pos, uint32_t value_bits, uint64_t* val_out) {
+    if (!ctx || !p || (value_bits != 64 && value_bits != 128)) return MZ_ERR_BAD_ARG;
+    mz_params q = *p;
+    q.value_bits = value_bits;
+    int rc = mz_params_validate(&q, n_bp);
+    if (rc) return rc;
+    if (n_pos == 0) return MZ_OK;
+    if (!packed || !pos || !val_out) return MZ_ERR_BAD_ARG;
+    DevState& d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    ctx->timing = mz_timing{};
+    const uint32_t vw = value_bits / 64;
+    const uint64_t byte_lo = bp_offset / 4 & ~uint64_t(3);
+    const size_t nbytes = (size_t)((bp_offset + n_bp + 3) / 4 - byte_lo);
+    const mz_ctx::Resident& rs = ctx->resident;
+    const bool have = rs.packed == packed && rs.bp_offset == bp_offset && rs.n_bp == n_bp && rs.byte_lo == byte_lo &&
+                      rs.nbytes == nbytes && d.in.cap >= nbytes;
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    if (!have) {
+        ctx->resident = mz_ctx::Resident{};
+        if ((rc = d.in.reserve(nbytes + 64))) return rc;
+        CK(cudaMemcpyAsync(d.in.p, packed + byte_lo, nbytes, cudaMemcpyHostToDevice, d.stream));
+    }
+    if ((rc = d.pos.reserve(n_pos))) return rc;
+    if ((rc = d.val.reserve(n_pos * vw))) return rc;
+    if ((rc = d.scratch.reserve(4))) return rc;
+    CK(cudaMemcpyAsync(d.pos.p, pos, n_pos * 4, cudaMemcpyHostToDevice, d.stream));
+    CK(cudaMemsetAsync(d.scratch.p, 0, 8, d.stream));
+    CK(cudaEventRecord(d.ev[1], d.stream));
+    mz::KArgs a{};
+    fill_input_args(a, q, d.in.p, bp_offset, byte_lo, nbytes, 0);
+    const unsigned nt = 256;
+    mz_values_kernel<<<(unsigned)((n_pos + nt - 1) / nt), nt, 0, d.stream>>>(a, d.pos.p, n_pos, n_bp, d.val.p,
+                                                                         reinterpret_cast<uint32_t*>(d.scratch.p));
+    CK(cudaGetLastError());
+    ctx->timing.kernel_launches++;
+    CK(cudaEventRecord(d.ev[2], d.stream));
+    uint32_t bad = 0;
+    CK(cudaMemcpyAsync(&bad, d.scratch.p, 4, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaMemcpyAsync(val_out, d.val.p, n_pos * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, d.ev[0], d.ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, d.ev[1], d.ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, d.ev[2], d.ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, d.ev[0], d.ev[3]);
+    if (!have) {  // the sequence is resident now
+        ctx->resident.packed = packed, ctx->resident.bp_offset = bp_offset, ctx->resident.n_bp = n_bp;
+        ctx->resident.byte_lo = byte_lo, ctx->resident.nbytes = nbytes;
+    }
+    return bad ? MZ_ERR_BAD_ARG : MZ_OK;
+}
+
+// Host <-> device copy rate of the context's devices, all at once: the ceiling of every
+// end-to-end number (one PCIe link per device, shared host memory / root complex).
+int mz_pcie_probe(mz_ctx* ctx, uint64_t bytes_per_device, uint32_t reps, mz_pcie_result* res) {
+    if (!ctx || !res || bytes_per_device == 0 || reps == 0) return MZ_ERR_BAD_ARG;
+    memset(res, 0, sizeof *res);
+    const size_t ndev = ctx->devs.size();
+    struct Bufs {
+        void *h_in = nullptr, *h_out = nullptr, *d_in = nullptr, *d_out = nullptr;
+    };
+    std::vector<Bufs> b(ndev);
+    int rc = MZ_OK;
+    auto cleanup = [&] {
+        for (size_t i = 0; i < ndev; i++) {
+            cudaSetDevice(ctx->devs[i].device);
+            if (b[i].h_in) cudaFreeHost(b[i].h_in);
+            if (b[i].h_out) cudaFreeHost(b[i].h_out);
+            if (b[i].d_in) cudaFree(b[i].d_in);
+            if (b[i].d_out) cudaFree(b[i].d_out);
+        }
+        cudaSetDevice(ctx->devs[0].device);
+    };
+    for (size_t i = 0; i < ndev && rc == MZ_OK; i++) {
+        cudaError_t e = cudaSetDevice(ctx->devs[i].device);
+        if (e == cudaSuccess) e = cudaHostAlloc(&b[i].h_in, bytes_per_device, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaHostAlloc(&b[i].h_out, bytes_per_device, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaMalloc(&b[i].d_in, bytes_per_device);
+        if (e == cudaSuccess) e = cudaMalloc(&b[i].d_out, bytes_per_device);
+        if (e == cudaSuccess) e = cudaMemset(b[i].d_out, 1, bytes_per_device);
+        if (e != cudaSuccess) rc = cuda_fail(e, "mz_pcie_probe setup", __LINE__);
+        else {
+            memset(b[i].h_in, 1, bytes_per_device);   // touch the pages
+            memset(b[i].h_out, 1, bytes_per_device);
+        }
+    }
+    // mode 0: H2D only, 1: D2H only, 2: both directions at once (slot 0 / slot 1 streams)
+    auto run = [&](int mode, double* h2d_gbs, double* d2h_gbs) -> int {
+        for (int pass = 0; pass < 2; pass++) {  // pass 0 warms up
+            const uint32_t n = pass ? reps : 1;
+            const auto t0 = std::chrono::steady_clock::now();
+            for (uint32_t r = 0; r < n; r++)
+                for (size_t i = 0; i < ndev; i++) {
+                    CK(cudaSetDevice(ctx->devs[i].device));
+                    if (mode != 1) CK(cudaMemcpyAsync(b[i].d_in, b[i].h_in, bytes_per_device, cudaMemcpyHostToDevice, ctx->slot(i, 0).stream));
+                    if (mode != 0) CK(cudaMemcpyAsync(b[i].h_out, b[i].d_out, bytes_per_device, cudaMemcpyDeviceToHost, ctx->slot(i, 1).stream));
+                }
+            for (size_t i = 0; i < ndev; i++) {
+                CK(cudaSetDevice(ctx->devs[i].device));
+                CK(cudaStreamSynchronize(ctx->slot(i, 0).stream));
+                CK(cudaStreamSynchronize(ctx->slot(i, 1).stream));
+            }
+            const double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            const double gbs = (double)bytes_per_device * n * ndev / s / 1e9;
+            if (pass) {
+                if (mode != 1) *h2d_gbs = gbs;
+                if (mode != 0) *d2h_gbs = gbs;
+            }
+        }
+        return MZ_OK;
+    };
+    if (rc == MZ_OK) rc = run(0, &res->h2d_gbs, nullptr);
+    if (rc == MZ_OK) rc = run(1, nullptr, &res->d2h_gbs);
+    if (rc == MZ_OK) rc = run(2, &res->bidir_h2d_gbs, &res->bidir_d2h_gbs);
+    res->n_devices = (uint32_t)ndev;
+    cleanup();
+    return rc;
+}
+
 int mz_last_timing(const mz_ctx* ctx, mz_timing* t) {
     if (!ctx || !t) return MZ_ERR_BAD_ARG;
     *t = ctx->timing;
@@ -1009,113 +1229,78 @@ static int run_host_impl(mz_ctx* ctx, const mz_params* p, const uint8_t* packed,
         if (!am.bits && n_bp) return MZ_ERR_BAD_ARG;
     }
     out->count = 0;
+    ctx->resident = mz_ctx::Resident{};
     const uint32_t l = p->k + p->w - 1;
     if (n_bp < l) return MZ_OK;
     if (!packed || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
     const uint64_t nwin = n_bp - l + 1;
-    const size_t ndev = std::min<uint64_t>(ctx->devs.size(), nwin);
+    const size_t ndev = ctx->devs.size();
     const uint32_t vw = p->value_bits / 64;  // u64 words per value
     ctx->timing = mz_timing{};
-    uint64_t pipe_min = 1ull << 26;
+    // Large inputs flow through the chunk pipeline (all devices of the context); small ones are
+    // one launch on the first device (sharding a few million windows costs more than it saves).
+    uint64_t pipe_min = ndev == 1 ? (1ull << 26) : (1ull << 23);
     if (const char* e = getenv("MZ_PIPELINE_MIN_WINDOWS")) pipe_min = strtoull(e, nullptr, 10);
-    if (ndev == 1 && nwin >= pipe_min && !getenv("MZ_NO_PIPELINE")) {
+    if (nwin >= pipe_min && !getenv("MZ_NO_PIPELINE")) {
         const auto t0 = std::chrono::steady_clock::now();
-        rc = run_pipelined(ctx, *p, packed, bp_offset, n_bp, am, out);
+        rc = run_pipelined(ctx, ndev, *p, packed, bp_offset, n_bp, am, out);
         ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
         return rc;
     }
 
-    struct Shard {
-        uint64_t wb, we, cap, count, byte_lo = 0, abyte_lo = 0;
-        size_t nbytes = 0, anbytes = 0;
-    };
-    // (re)launch shard s on its device with the output capacity s.cap
-    auto launch_shard = [&](DevState& d, Shard& s) -> int {
-        int r;
-        if ((r = d.pos.reserve(s.cap))) return r;
-        if (p->want_sk && (r = d.sk.reserve(s.cap))) return r;
-        if (vw && (r = d.val.reserve(s.cap * vw))) return r;
+    DevState& d = ctx->devs[0];
+    CK(cudaSetDevice(d.device));
+    struct SyncOnExit {  // error paths: nothing may still write the caller's arrays
+        DevState& d;
+        ~SyncOnExit() {
+            cudaStreamSynchronize(d.stream);
+            cudaGetLastError();
+        }
+    } sync_on_exit{d};
+    uint64_t cap = estimate_capacity(*p, nwin);
+    uint64_t abyte_lo = 0;
+    size_t anbytes = 0;
+    const uint64_t byte_lo = bp_offset / 4 & ~uint64_t(3);
+    const size_t nbytes = (size_t)((bp_offset + n_bp + 3) / 4 - byte_lo);
+    if ((rc = d.in.reserve(nbytes + 64))) return rc;
+    CK(cudaEventRecord(d.ev[0], d.stream));
+    CK(cudaMemcpyAsync(d.in.p, packed + byte_lo, nbytes, cudaMemcpyHostToDevice, d.stream));
+    if (am.bits && (rc = upload_amb(d, am, 0, n_bp, &abyte_lo, &anbytes))) return rc;
+    CK(cudaEventRecord(d.ev[1], d.stream));
+    for (int attempt = 0;; attempt++) {  // a too small capacity estimate is re-run with the exact count
+        if ((rc = d.pos.reserve(cap))) return rc;
+        if (p->want_sk && (rc = d.sk.reserve(cap))) return rc;
+        if (vw && (rc = d.val.reserve(cap * vw))) return rc;
         mz::KArgs a{};
-        fill_input_args(a, *p, d.in.p, bp_offset, s.byte_lo, s.nbytes, nwin);
-        if (am.bits) fill_amb_args(a, am, d.amb.p, s.abyte_lo, s.anbytes);
-        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = s.cap;
-        if ((r = enqueue_run(d, *p, a, s.wb, s.we, &ctx->timing.kernel_launches))) return r;
+        fill_input_args(a, *p, d.in.p, bp_offset, byte_lo, nbytes, nwin);
+        if (am.bits) fill_amb_args(a, am, d.amb.p, abyte_lo, anbytes);
+        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = cap;
+        if ((rc = enqueue_run(d, *p, a, 0, nwin, &ctx->timing.kernel_launches))) return rc;
         CK(cudaEventRecord(d.ev[2], d.stream));
-        return MZ_OK;
-    };
-    std::vector<Shard> sh(ndev);
-    const uint64_t per = (nwin + ndev - 1) / ndev;
-
-    // phase 1: H2D + kernel on every device
-    for (size_t i = 0; i < ndev; i++) {
-        DevState& d = ctx->devs[i];
-        Shard& s = sh[i];
-        s.wb = per * i;
-        s.we = std::min<uint64_t>(s.wb + per, nwin);
-        s.cap = estimate_capacity(*p, s.we - s.wb);
-        CK(cudaSetDevice(d.device));
-        // bases [blo, bhi) of the sequence are needed: one extra window on the left
-        const uint64_t blo = s.wb > 0 ? s.wb - 1 : 0;
-        const uint64_t bhi = s.we + l - 1;
-        s.byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
-        s.nbytes = (size_t)((bp_offset + bhi + 3) / 4 - s.byte_lo);
-        if ((rc = d.in.reserve(s.nbytes + 64))) return rc;
-        CK(cudaEventRecord(d.ev[0], d.stream));
-        CK(cudaMemcpyAsync(d.in.p, packed + s.byte_lo, s.nbytes, cudaMemcpyHostToDevice, d.stream));
-        if (am.bits && (rc = upload_amb(d, am, blo, bhi, &s.abyte_lo, &s.anbytes))) return rc;
-        CK(cudaEventRecord(d.ev[1], d.stream));
-        if ((rc = launch_shard(d, s))) return rc;
-    }
-    // phase 2: counts; re-run a shard whose capacity estimate was too small
-    uint64_t total = 0;
-    for (size_t i = 0; i < ndev; i++) {
-        DevState& d = ctx->devs[i];
-        Shard& s = sh[i];
-        CK(cudaSetDevice(d.device));
         CK(cudaStreamSynchronize(d.stream));
-        s.count = d.hs->count;
-        if (d.hs->overflow) {
-            s.cap = s.count;
-            if ((rc = launch_shard(d, s))) return rc;
-            CK(cudaStreamSynchronize(d.stream));
-            if (d.hs->overflow) {
-                g_last_error = "internal: exact-capacity re-run overflowed";
-                return MZ_ERR_CUDA;
-            }
-            s.count = d.hs->count;
+        if (!d.hs->overflow) break;
+        if (attempt == 1) {
+            g_last_error = "internal: exact-capacity re-run overflowed";
+            return MZ_ERR_CUDA;
         }
-        total += s.count;
+        cap = d.hs->count;
     }
-    out->count = total;
-    if (total > out->capacity) return MZ_ERR_CAPACITY;
-    // phase 3: ordered gather into the caller's arrays
-    uint64_t off = 0;
-    for (size_t i = 0; i < ndev; i++) {
-        DevState& d = ctx->devs[i];
-        Shard& s = sh[i];
-        CK(cudaSetDevice(d.device));
-        if (s.count) {
-            CK(cudaMemcpyAsync(out->pos + off, d.pos.p, s.count * 4, cudaMemcpyDeviceToHost, d.stream));
-            if (p->want_sk) CK(cudaMemcpyAsync(out->sk + off, d.sk.p, s.count * 4, cudaMemcpyDeviceToHost, d.stream));
-            if (vw) CK(cudaMemcpyAsync(out->val + off * vw, d.val.p, s.count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
-        }
-        CK(cudaEventRecord(d.ev[3], d.stream));
-        off += s.count;
+    const uint64_t count = d.hs->count;
+    out->count = count;
+    if (count > out->capacity) return MZ_ERR_CAPACITY;
+    if (count) {
+        CK(cudaMemcpyAsync(out->pos, d.pos.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (p->want_sk) CK(cudaMemcpyAsync(out->sk, d.sk.p, count * 4, cudaMemcpyDeviceToHost, d.stream));
+        if (vw) CK(cudaMemcpyAsync(out->val, d.val.p, count * 8 * vw, cudaMemcpyDeviceToHost, d.stream));
     }
-    for (size_t i = 0; i < ndev; i++) {
-        DevState& d = ctx->devs[i];
-        CK(cudaSetDevice(d.device));
-        CK(cudaStreamSynchronize(d.stream));
-        float h2d = 0, ker = 0, d2h = 0, tot = 0;
-        cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
-        cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
-        cudaEventElapsedTime(&d2h, d.ev[2], d.ev[3]);
-        cudaEventElapsedTime(&tot, d.ev[0], d.ev[3]);
-        ctx->timing.h2d_ms = std::max(ctx->timing.h2d_ms, h2d);
-        ctx->timing.kernel_ms = std::max(ctx->timing.kernel_ms, ker);
-        ctx->timing.d2h_ms = std::max(ctx->timing.d2h_ms, d2h);
-        ctx->timing.total_ms = std::max(ctx->timing.total_ms, tot);
-    }
+    CK(cudaEventRecord(d.ev[3], d.stream));
+    CK(cudaStreamSynchronize(d.stream));
+    cudaEventElapsedTime(&ctx->timing.h2d_ms, d.ev[0], d.ev[1]);
+    cudaEventElapsedTime(&ctx->timing.kernel_ms, d.ev[1], d.ev[2]);
+    cudaEventElapsedTime(&ctx->timing.d2h_ms, d.ev[2], d.ev[3]);
+    cudaEventElapsedTime(&ctx->timing.total_ms, d.ev[0], d.ev[3]);
+    ctx->resident.packed = packed, ctx->resident.bp_offset = bp_offset, ctx->resident.n_bp = n_bp;
+    ctx->resident.byte_lo = byte_lo, ctx->resident.nbytes = nbytes;
     return MZ_OK;
 }
 
@@ -1136,6 +1321,7 @@ static int pack_ascii_impl(mz_ctx* ctx, const char* ascii, uint64_t n, uint8_t* 
                            uint8_t* amb_out, bool want_amb) {
     if (!ctx || (n && (!ascii || !packed_out || (want_amb && !amb_out)))) return MZ_ERR_BAD_ARG;
     if (n == 0) return MZ_OK;
+    ctx->resident = mz_ctx::Resident{};
     DevState& d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
     ctx->timing = mz_timing{};
@@ -1170,6 +1356,7 @@ static int run_ascii_impl(mz_ctx* ctx, const mz_params* p, const char* ascii, ui
     const uint32_t l = p->k + p->w - 1;
     if (n < l) return MZ_OK;
     if (!ascii || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
+    ctx->resident = mz_ctx::Resident{};
     DevState& d = ctx->devs[0];
     CK(cudaSetDevice(d.device));
     ctx->timing = mz_timing{};
@@ -1224,6 +1411,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     if ((read_start_bp == nullptr) != (read_len_bp == nullptr)) return MZ_ERR_BAD_ARG;
     out->count = 0;
     out_offsets[0] = 0;
+    ctx->resident = mz_ctx::Resident{};
     if (n_reads == 0) return MZ_OK;
     const uint32_t l = p->k + p->w - 1;
     uint32_t max_len = fixed_len_bp;
@@ -1254,6 +1442,23 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     CK(cudaSetDevice(ctx->devs[0].device));
     ctx->timing = mz_timing{};
     const auto t_begin = std::chrono::steady_clock::now();
+    // Reads are independent units: chunk c of the read list runs on device c % ndev (no halo, no
+    // seam), CSR offsets are chunk-local on the device and rebased on the way out.
+    const uint64_t ND = ctx->devs.size();
+    auto dev_of = [&](uint64_t c) { return (size_t)(c % ND); };
+    auto slot_of = [&](uint64_t c) { return (int)((c / ND) % kSlots); };
+    struct SyncAll {  // error paths: nothing may still write the caller's arrays
+        mz_ctx* ctx;
+        ~SyncAll() {
+            for (size_t i = 0; i < ctx->devs.size(); i++)
+                for (int sl = 0; sl < kSlots; sl++) {
+                    DevState& d = ctx->slot(i, sl);
+                    if (cudaSetDevice(d.device) == cudaSuccess) cudaStreamSynchronize(d.stream);
+                }
+            cudaGetLastError();
+            cudaSetDevice(ctx->devs[0].device);
+        }
+    } sync_all{ctx};
 
     // Geometry.  A thread handles one read when the longest read fits the per-thread record of
     // the chosen kernel; otherwise reads are cut into pieces of S windows (each piece a thread,
@@ -1283,7 +1488,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     // Reads are processed in chunks that flow through kSlots streams (H2D of chunk c+1 | kernel
     // of c | D2H of c-1 | host copy-out of c-2), like the single-sequence path.  Reads that are
     // not stored in order cannot be streamed: one chunk.
-    uint64_t chunk_reads = std::max<uint64_t>(1, (64ull << 20) / std::max<uint64_t>(1, packed_bytes / n_reads + 1));
+    // ~64 MB of packed input per chunk, smaller (>= 8 MB) when that leaves a device of the context
+    // with fewer than four chunks
+    const uint64_t chunk_bytes = std::min<uint64_t>(64ull << 20, std::max<uint64_t>(8ull << 20, packed_bytes / (4 * ctx->devs.size())));
+    uint64_t chunk_reads = std::max<uint64_t>(1, chunk_bytes / std::max<uint64_t>(1, packed_bytes / n_reads + 1));
     if (const char* e = getenv("MZ_BATCH_CHUNK_READS")) chunk_reads = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
     chunk_reads = (chunk_reads + 15) & ~uint64_t(15);
     if (!monotone || chunk_reads > n_reads) chunk_reads = n_reads;
@@ -1341,9 +1549,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     };
 
     auto issue = [&](uint64_t c) -> int {
-        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
         BJob& j = jobs[c];
         int r;
+        CK(cudaSetDevice(d.device));
         j.r0 = c * chunk_reads;
         j.r1 = std::min<uint64_t>(j.r0 + chunk_reads, n_reads);
         const uint64_t nr = j.r1 - j.r0;
@@ -1449,9 +1658,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     };
     // kernel done -> counts known -> D2H of this chunk's outputs and CSR offsets
     auto retire = [&](uint64_t c) -> int {
-        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
         BJob& j = jobs[c];
         int r;
+        CK(cudaSetDevice(d.device));
         CK(cudaStreamSynchronize(d.stream));
         float h2d = 0, ker = 0;
         cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
@@ -1498,9 +1708,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     };
     // D2H done -> copy out of the bounce buffers, rebase the CSR offsets
     auto finish = [&](uint64_t c) -> int {
-        DevState& d = ctx->slot(0, (int)(c % kSlots));
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
         BJob& j = jobs[c];
         if (too_small) return MZ_OK;
+        CK(cudaSetDevice(d.device));
         CK(cudaEventSynchronize(d.ev[3]));
         float d2h = 0;
         cudaEventElapsedTime(&d2h, d.ev[2], d.ev[3]);
@@ -1517,12 +1728,11 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         std::vector<uint32_t>().swap(j.piece_win0);
         return MZ_OK;
     };
-    for (uint64_t c = 0; c < nchunks + 2; c++) {
+    for (uint64_t c = 0; c < nchunks + 2 * ND; c++) {
         if (c < nchunks && (rc = issue(c))) return rc;
-        if (c >= 1 && c - 1 < nchunks && (rc = retire(c - 1))) return rc;
-        if (c >= 2 && (rc = finish(c - 2))) return rc;
+        if (c >= ND && c - ND < nchunks && (rc = retire(c - ND))) return rc;
+        if (c >= 2 * ND && (rc = finish(c - 2 * ND))) return rc;
     }
-    for (int sl = 0; sl < kSlots; sl++) CK(cudaStreamSynchronize(ctx->slot(0, sl).stream));
     ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     out->count = total;
     return too_small ? MZ_ERR_CAPACITY : MZ_OK;

@@ -40,9 +40,15 @@ def _check(sm, oracle, packed, amb, off, n, k, w, mode, kind="nt"):
     assert np.array_equal(pos.array, want), tag
     length = k if mode == 0 else k + w - 1
     if length <= 32:
-        assert np.array_equal(out.values_u64(), oracle.values_u64(packed, off, length, True, want)), tag
+        wv = oracle.values_u64(packed, off, length, True, want)
+        assert np.array_equal(out.values_u64(), wv), tag
+        fpos, _, fval = b.run_with_values(nseq, 64, skip_ambiguous=True)
+        assert np.array_equal(fpos, want) and np.array_equal(fval, wv), tag
     elif length <= 64:
-        assert np.array_equal(out._values(128), oracle.values_u128(packed, off, length, True, want)), tag
+        wv = oracle.values_u128(packed, off, length, True, want)
+        assert np.array_equal(out._values(128), wv), tag
+        fpos, _, fval = b.run_with_values(nseq, 128, skip_ambiguous=True)
+        assert np.array_equal(fpos, want) and np.array_equal(fval, wv), tag
     return want
 
 
@@ -185,6 +191,8 @@ def test_skip_ambiguous_large_pipelined_and_device(sm, oracle, monkeypatch):
         out = sm.canonical_minimizers(k, w).run_skip_ambiguous_windows(nseq, pos)
         assert np.array_equal(pos.array, want)
         assert np.array_equal(out.values_u64(), wantv)
+        fpos, _, fval = sm.canonical_minimizers(k, w).run_with_values(nseq, 64, skip_ambiguous=True)
+        assert np.array_equal(fpos, want) and np.array_equal(fval, wantv)
     monkeypatch.delenv("MZ_CHUNK_WINDOWS")
     monkeypatch.delenv("MZ_PIPELINE_MIN_WINDOWS")
     # closed syncmers on the same input

@@ -40,11 +40,18 @@ def _check_case(sm, oracle, packed, off, n, k, w, canonical, mode, kind="nt", ha
     if mode == 0:
         assert np.array_equal(sk.array, esk), tag
     length = k if mode == 0 else k + w - 1
+    # values twice: the lazy Output iterator (mz_values) and fused into the run (value_bits)
     if length <= 32:
-        assert np.array_equal(out.values_u64(), oracle.values_u64(packed, off, length, canonical, epos)), tag
+        want = oracle.values_u64(packed, off, length, canonical, epos)
+        assert np.array_equal(out.values_u64(), want), tag
+        fpos, fsk, fval = (b.super_kmers(sm.U32Vec()) if mode == 0 else b).run_with_values(seq, 64)
+        assert np.array_equal(fpos, epos) and np.array_equal(fval, want), tag
+        assert mode != 0 or np.array_equal(fsk, esk), tag
     elif length <= 64:
-        got = out._values(128)
-        assert np.array_equal(got, oracle.values_u128(packed, off, length, canonical, epos)), tag
+        want = oracle.values_u128(packed, off, length, canonical, epos)
+        assert np.array_equal(out._values(128), want), tag
+        fpos, _, fval = b.run_with_values(seq, 128)
+        assert np.array_equal(fpos, epos) and np.array_equal(fval, want), tag
 
 
 def test_reference_golden_vectors(sm):
@@ -166,6 +173,84 @@ def test_append_semantics(sm, oracle):
     v = sm.U32Vec([int(first[0])])
     sm.minimizers(7, 5).run(s, v)
     assert v.tolist() == first.tolist()
+
+
+def test_lazy_values_cover_the_whole_vector(sm, oracle):
+    """Output::values_* iterate ALL of min_pos (src/lib.rs:598-612), including positions appended
+    by earlier runs; positions whose k-mer runs past the sequence are an error (read_kmer asserts)."""
+    n, k, w = 5000, 21, 11
+    packed = oracle.synth_packed(5, n + 4)
+    seq = sm.PackedSeq(packed, 1, n)
+    v = sm.U32Vec([7, 100])
+    out = sm.canonical_minimizers(k, w).run(seq, v)
+    assert v.tolist()[:2] == [7, 100] and len(v) > 2
+    assert np.array_equal(out.values_u64(), oracle.values_u64(packed, 1, k, True, v.array))
+    got = out.values_u128()
+    want = oracle.values_u128(packed, 1, k, True, v.array)
+    assert got == [int(lo) | (int(hi) << 64) for lo, hi in want]
+    pv = out.pos_and_values_u64()
+    assert [a for a, _ in pv] == v.tolist()
+    bad = sm.U32Vec([n - k + 1])
+    with pytest.raises(sm.MzError):
+        sm.Output(sm.canonical_minimizers(k, w), seq, bad).values_u64()
+    # forward builder: plain k-mers; syncmers: l-mers
+    v2 = sm.U32Vec()
+    o2 = sm.closed_syncmers(9, 5).run(seq, v2)
+    assert np.array_equal(o2.values_u64(), oracle.values_u64(packed, 1, 13, False, v2.array))
+
+
+def test_run_scalar_overwrites(sm, oracle):
+    """run_scalar / run_scalar_once (src/lib.rs:358-378, 504-533): same results, but the scalar
+    collectors overwrite the vectors from index 0 (src/collect.rs:15-76) instead of appending."""
+    n = 3000
+    packed = oracle.synth_packed(77, n + 4)
+    seq = sm.PackedSeq(packed, 2, n)
+    for (k, w, canonical, mode) in ((21, 11, True, 0), (7, 5, False, 0), (9, 5, False, 1), (9, 5, True, 2)):
+        b = _builder(sm, k, w, canonical, mode)
+        pr = oracle.make_params(k, w, canonical=canonical, mode=mode)
+        epos, esk = oracle.run(packed, 2, n, pr, "stream", want_sk=(mode == 0))
+        assert np.array_equal(b.run_scalar_once(seq), epos)
+        v = sm.U32Vec([1, 2, 3])
+        out = b.run_scalar(seq, v)
+        assert np.array_equal(v.array, epos)
+        assert len(out.values_u64()) == len(epos)
+        if mode == 0:
+            sk = sm.U32Vec([9, 9])
+            v = sm.U32Vec([4])
+            b.super_kmers(sk).run_scalar(seq, v)
+            assert np.array_equal(v.array, epos) and np.array_equal(sk.array, esk)
+            assert np.array_equal(b.super_kmers(sm.U32Vec()).run_scalar_once(seq), epos)
+    # too short: output cleared, index vector untouched (src/collect.rs:45-48)
+    v, sk = sm.U32Vec([5]), sm.U32Vec([6])
+    sm.minimizers(7, 5).super_kmers(sk).run_scalar(sm.PackedSeq(packed, 0, 8), v)
+    assert v.tolist() == [] and sk.tolist() == [6]
+
+
+def test_table_hashers(sm, oracle):
+    """Hashers cross the ABI as their per-base tables (mz_params_set_tables): the built-in
+    NtHasher tables passed explicitly give the built-in result; arbitrary (seeded-like) tables
+    agree with the oracle run on the same tables."""
+    n = 20000
+    packed = oracle.synth_packed(3, n + 4)
+    seq = sm.PackedSeq(packed, 0, n)
+    F = [0x95c60474, 0x62a02b4c, 0x82572324, 0x4be24456]
+    Cc = [F[b ^ 2] for b in range(4)]
+    a = sm.canonical_minimizers(31, 19).run_once(seq)
+    b = sm.canonical_minimizers(31, 19).hasher(sm.NtHasher.from_tables(31, F, Cc, 7, True)).run_once(seq)
+    assert np.array_equal(a, b)
+    rng = np.random.default_rng(11)
+    for rot in (7, 1, 13):
+        f = [int(x) for x in rng.integers(0, 2**32, 4)]
+        c = [f[b ^ 2] for b in range(4)]
+        for canonical in (False, True):
+            h = oracle.make_hasher_tables(f, c, rot, canonical)
+            pr = oracle.make_params(21, 11, canonical=canonical, hasher=h)
+            want, _ = oracle.run(packed, 0, n, pr, "stream")
+            got = (sm.canonical_minimizers if canonical else sm.minimizers)(21, 11).hasher(
+                sm.NtHasher.from_tables(21, f, c, rot, canonical)).run_once(seq)
+            assert np.array_equal(got, want), (rot, canonical)
+    with pytest.raises(NotImplementedError):
+        sm.MulHasher.new_with_seed(21, 1234)
 
 
 def test_medium_exact_and_rc_symmetry(sm, oracle):
@@ -335,10 +420,14 @@ def test_full_size_genome_properties(sm, oracle):
     packed, off = bench.synth_packed_range(bench.SEED, 0, n)
     packed = np.ascontiguousarray(packed)
     seq = sm.PackedSeq(packed, off, n)
+    # positions, super-k-mer starts and values fused through the chunk pipeline ...
+    p, s, vals = sm.canonical_minimizers(k, w).super_kmers(sm.U32Vec()).run_with_values(seq, 64)
+    # ... and the same through the reference-shaped calls: positions only, lazy values (mz_values)
     pos, sk = sm.U32Vec(), sm.U32Vec()
     out = sm.canonical_minimizers(k, w).super_kmers(sk).run(seq, pos)
-    vals = out.values_u64()
-    p, s = pos.array, sk.array
+    assert np.array_equal(pos.array, p) and np.array_equal(sk.array, s)
+    assert np.array_equal(out.values_u64(), vals)
+    del pos, sk, out
     m = len(p)
     assert len(s) == m and len(vals) == m
     assert abs(m / n - 2.0 / (w + 1)) < 0.002                      # density of random minimizers
