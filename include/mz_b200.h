@@ -234,6 +234,19 @@ typedef struct mz_pcie_result {
 } mz_pcie_result;
 int mz_pcie_probe(mz_ctx* ctx, uint64_t bytes_per_device, uint32_t reps, mz_pcie_result* res);
 
+/*
+ * mz_alu_probe -- measured INT32 ALU-pipe peak of device `dev_index` of the context: lane-ops per
+ * second of a LOP3 / SHF / VIMNMX / PRMT mix (the instruction mix of the window-minimum loop) with
+ * eight independent chains per thread on every SM, no memory traffic.  The minimizer kernels are
+ * bound by this pipe, not by HBM; bench.py divides the kernels' integer work by it (alu_roofline).
+ */
+typedef struct mz_alu_result {
+    double lane_ops_per_s; /* 32 lanes x warp instructions retired on the ALU pipe per second      */
+    float ms;              /* duration of the probe launch                                         */
+    uint32_t sm_count;
+} mz_alu_result;
+int mz_alu_probe(mz_ctx* ctx, int dev_index, mz_alu_result* res);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,15 +19,19 @@
 
 #if defined(__AVX2__)
 
+/* Per-lane output region: lane i collects into its own eighth of the caller's slice (the
+ * reference keeps one Vec per lane in a thread-local cache, src/collect.rs:124-126, and flattens
+ * them in order afterwards, :252-272); nothing is allocated while the lanes run. */
 typedef struct {
     uint32_t* p;
     uint64_t n, cap;
+    int overflow;
 } lanebuf;
 
 static inline void lb_push(lanebuf* b, uint32_t v) {
     if (b->n == b->cap) {
-        b->cap = b->cap ? b->cap * 2 : 1024;
-        b->p = (uint32_t*)realloc(b->p, b->cap * sizeof(uint32_t));
+        b->overflow = 1;
+        return;
     }
     b->p[b->n++] = v;
 }
@@ -126,6 +130,11 @@ static uint64_t run_range_avx2(const uint8_t* packed, uint64_t off, uint64_t n, 
     lanebuf lb[8], lsk[8];
     memset(lb, 0, sizeof lb);
     memset(lsk, 0, sizeof lsk);
+    const uint64_t lcap = cap / 8;
+    for (int i = 0; i < 8; i++) {
+        lb[i].p = pos_out + (uint64_t)i * lcap, lb[i].cap = lcap;
+        if (sk_out) lsk[i].p = sk_out + (uint64_t)i * lcap, lsk[i].cap = lcap;
+    }
 
     const uint64_t nsteps = Lw + l - 1; /* bases per lane */
     /* 16-bit positions inside the packed elements are re-based like the reference does
@@ -208,21 +217,17 @@ static uint64_t run_range_avx2(const uint8_t* packed, uint64_t off, uint64_t n, 
         }
     }
     free(ringl);
+    /* flatten the lanes in order (in place: lane i never starts left of what is already flat) */
     uint64_t total = 0;
-    int ok = 1;
     for (int i = 0; i < 8; i++) {
+        if (lb[i].overflow) return (uint64_t)-1;
         uint64_t skip = (total > 0 && lb[i].n > 0 && lb[i].p[0] == pos_out[total - 1]) ? 1 : 0;
         uint64_t cntl = lb[i].n - skip;
-        if (total + cntl > cap) {
-            ok = 0;
-            break;
-        }
-        if (cntl) memcpy(pos_out + total, lb[i].p + skip, cntl * 4);
-        if (sk_out && cntl) memcpy(sk_out + total, lsk[i].p + skip, cntl * 4);
+        if (cntl) memmove(pos_out + total, lb[i].p + skip, cntl * 4);
+        if (sk_out && cntl) memmove(sk_out + total, lsk[i].p + skip, cntl * 4);
         total += cntl;
     }
-    for (int i = 0; i < 8; i++) free(lb[i].p), free(lsk[i].p);
-    return ok ? total : (uint64_t)-1;
+    return total;
 }
 #endif /* __AVX2__ */
 
@@ -298,6 +303,67 @@ static void* bworker(void* arg) {
     return NULL;
 }
 
+/* Timed CPU arm: like mzb_run_mt, but every thread writes straight into its own slice of the
+ * caller's pre-allocated (and pre-faulted) arrays -- slice t = entries [t * cap / threads, ...) --
+ * and nothing is concatenated afterwards, which is what the reference's own multi-threaded
+ * benchmark does (thread-local output Vec per rayon worker, bench/src/bin/paper.rs:439-461).
+ * The logical output is the concatenation of [starts_out[t], starts_out[t] + counts_out[t]) for
+ * t = 0 .. threads-1 (a thread's first entry is dropped when it repeats the previous thread's
+ * last one: the flatten rule).  No allocation of output memory inside.  Returns the total count. */
+uint64_t mzb_run_mt_slices(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_params* p, int threads,
+                           uint32_t* pos, uint32_t* sk, uint64_t* val, uint64_t cap, uint64_t* starts_out,
+                           uint64_t* counts_out) {
+    const uint32_t l = p->k + p->w - 1;
+    if (p->k == 0 || p->w == 0 || p->w >= (1u << 15) || n >= (1ull << 32)) return (uint64_t)-1;
+    if (p->strand_tiebreak && ((l & 1u) == 0 || !p->hasher.canonical)) return (uint64_t)-1;
+    if (threads < 1) threads = 1;
+    for (int t = 0; t < threads; t++) starts_out[t] = counts_out[t] = 0;
+    if (n < l) return 0;
+    const uint64_t nwin = n - l + 1;
+    int use_avx2 = mzb_have_avx2() && p->mode == MZO_MINIMIZER && p->hasher.rot == 7;
+    if (p->mode != MZO_MINIMIZER || p->k > 32) val = NULL;
+    int nt = threads;
+    if ((uint64_t)nt * 256 > nwin) nt = (int)(nwin / 256 ? nwin / 256 : 1);
+    bjob* jobs = (bjob*)calloc((size_t)nt, sizeof(bjob));
+    pthread_t* th = (pthread_t*)calloc((size_t)nt, sizeof(pthread_t));
+    const uint64_t per = (nwin + (uint64_t)nt - 1) / (uint64_t)nt, slice = cap / (uint64_t)nt;
+    for (int t = 0; t < nt; t++) {
+        bjob* j = &jobs[t];
+        j->packed = packed, j->off = off, j->n = n, j->p = p, j->use_avx2 = use_avx2;
+        j->wb = per * (uint64_t)t;
+        j->we = j->wb + per < nwin ? j->wb + per : nwin;
+        if (j->wb > j->we) j->wb = j->we;
+        j->cap = slice;
+        j->pos = pos + slice * (uint64_t)t;
+        j->sk = sk ? sk + slice * (uint64_t)t : NULL;
+        j->val = val ? val + slice * (uint64_t)t : NULL;
+    }
+    if (nt == 1) bworker(&jobs[0]);
+    else {
+        for (int t = 0; t < nt; t++) pthread_create(&th[t], NULL, bworker, &jobs[t]);
+        for (int t = 0; t < nt; t++) pthread_join(th[t], NULL);
+    }
+    uint64_t m = 0;
+    uint32_t last = 0;
+    int have_last = 0, ok = 1;
+    for (int t = 0; t < nt; t++) {
+        bjob* j = &jobs[t];
+        if (j->wb == j->we) continue;
+        if (j->count == (uint64_t)-1) {
+            ok = 0;
+            break;
+        }
+        const uint64_t skip = (use_avx2 && have_last && j->count > 0 && j->pos[0] == last) ? 1 : 0;
+        starts_out[t] = slice * (uint64_t)t + skip;
+        counts_out[t] = j->count - skip;
+        if (j->count) last = j->pos[j->count - 1], have_last = 1;
+        m += counts_out[t];
+    }
+    free(jobs);
+    free(th);
+    return ok ? m : (uint64_t)-1;
+}
+
 /* Multi-threaded baseline: contiguous window ranges per thread (analogue of the reference
  * benchmark's rayon loop, bench/src/bin/paper.rs:442-459), 8 AVX2 lanes inside each thread.
  * The packed buffer must be readable 16 bytes past its last base. Returns count or -1. */
@@ -324,7 +390,8 @@ uint64_t mzb_run_mt(const uint8_t* packed, uint64_t off, uint64_t n, const mzo_p
         if (j->wb > j->we) j->wb = j->we;
         const uint64_t range = j->we - j->wb;
         const uint64_t est = range / (p->w + 1) * 3 + 4096;
-        j->cap = (range < (1u << 20) || est > range) ? range : est;
+        /* worst case (every window emits): 8 lanes of ceil16(range / 8) windows each */
+        j->cap = (range < (1u << 20) || est > range) ? 8 * (((range + 7) / 8 + 15) / 16 * 16) : est;
         j->pos = (uint32_t*)malloc(4 * (j->cap + 1));
         j->sk = sk_out ? (uint32_t*)malloc(4 * (j->cap + 1)) : NULL;
         j->val = val_out ? (uint64_t*)malloc(8 * (j->cap + 1)) : NULL;

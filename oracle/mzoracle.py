@@ -85,6 +85,9 @@ def lib():
         L.mzo_run_reads.restype = C.c_uint64
         L.mzb_run_mt.argtypes = L.mzo_run_mt.argtypes
         L.mzb_run_mt.restype = C.c_uint64
+        L.mzb_run_mt_slices.argtypes = [u8p, C.c_uint64, C.c_uint64, C.POINTER(Params), C.c_int, u32p,
+                                        u32p, u64p, C.c_uint64, u64p, u64p]
+        L.mzb_run_mt_slices.restype = C.c_uint64
         L.mzb_have_avx2.restype = C.c_int
         _lib = L
     return _lib
@@ -249,6 +252,19 @@ def baseline_run_mt(packed, off, n, params: Params, threads: int, want_sk=False,
     if m == ERR:
         raise ValueError("baseline: run failed (parameters or capacity)")
     return pos[:m], (sk[:m] if want_sk else None), (val[:m] if want_val else None)
+
+
+def baseline_run_mt_slices(packed, off, n, params: Params, threads: int, pos, sk, val):
+    """Timed CPU arm: every thread writes into its own slice of the pre-allocated arrays
+    (pos / sk / val, sk and val may be None); returns (total, starts, counts) -- the logical
+    output is the concatenation of pos[starts[t]:starts[t]+counts[t]]."""
+    starts = np.zeros(threads, dtype=np.uint64)
+    counts = np.zeros(threads, dtype=np.uint64)
+    m = lib().mzb_run_mt_slices(_ptr(packed), off, n, C.byref(params), threads, _ptr(pos), _ptr(sk),
+                                _ptr(val), len(pos), _ptr(starts), _ptr(counts))
+    if m == ERR:
+        raise ValueError("baseline: run failed (parameters or slice capacity)")
+    return int(m), starts, counts
 
 
 def have_avx2() -> bool:

@@ -29,7 +29,7 @@ SYMBOLS = [
     "mz_ctx_create", "mz_ctx_destroy", "mz_ctx_device_count", "mz_host_alloc", "mz_host_free",
     "mz_run", "mz_run_device", "mz_run_batch", "mz_pack_ascii", "mz_run_ascii", "mz_last_timing",
     "mz_run_skip_ambiguous", "mz_run_device_skip_ambiguous", "mz_pack_ascii_n",
-    "mz_run_ascii_skip_ambiguous", "mz_params_set_tables", "mz_values", "mz_pcie_probe",
+    "mz_run_ascii_skip_ambiguous", "mz_params_set_tables", "mz_values", "mz_pcie_probe", "mz_alu_probe",
 ]
 
 
@@ -53,6 +53,10 @@ class MzTiming(C.Structure):
 class MzPcieResult(C.Structure):
     _fields_ = [("h2d_gbs", C.c_double), ("d2h_gbs", C.c_double), ("bidir_h2d_gbs", C.c_double),
                 ("bidir_d2h_gbs", C.c_double), ("n_devices", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class MzAluResult(C.Structure):
+    _fields_ = [("lane_ops_per_s", C.c_double), ("ms", C.c_float), ("sm_count", C.c_uint32)]
 
 
 class MzError(RuntimeError):
@@ -112,6 +116,7 @@ def lib():
                                        C.c_uint32, C.c_uint32]
     L.mz_values.argtypes = [vp, C.POINTER(MzParams), vp, C.c_uint64, C.c_uint64, vp, C.c_uint64,
                             C.c_uint32, vp]
+    L.mz_alu_probe.argtypes = [vp, C.c_int, C.POINTER(MzAluResult)]
     L.mz_pcie_probe.argtypes = [vp, C.c_uint64, C.c_uint32, C.POINTER(MzPcieResult)]
     _lib = L
     return L
