@@ -442,6 +442,11 @@ __global__ void mz_delta_encode_kernel(const uint32_t* __restrict__ v, uint64_t 
         delta[i] = (int8_t)(int32_t)(v[i] - v[i - 1]);
     }
 }
+}  // namespace
+namespace mz {
+void delta_decode_blocks(const int8_t* delta, const uint32_t* base, uint64_t n, uint64_t b0, uint64_t b1, uint32_t* out);  // mz_host_codec.cpp
+}
+namespace {
 size_t delta_bytes(uint64_t n) {  // [deltas, padded to 4][bases]
     return (size_t)((n + 3) & ~uint64_t(3)) + (size_t)((n + kDeltaBlock - 1) / kDeltaBlock) * 4;
 }
@@ -451,17 +456,7 @@ void delta_decode(const unsigned char* enc, uint64_t n, uint32_t* out, unsigned 
     const uint64_t nblk = (n + kDeltaBlock - 1) / kDeltaBlock;
     unsigned nt = max_threads ? std::min(max_threads, host_threads()) : host_threads();
     if (nblk < 64) nt = 1;
-    auto work = [=](uint64_t b0, uint64_t b1) {
-        for (uint64_t b = b0; b < b1; b++) {
-            const uint64_t lo = b * kDeltaBlock, hi = std::min<uint64_t>(lo + kDeltaBlock, n);
-            uint32_t v = base[b];
-            out[lo] = v;
-            for (uint64_t i = lo + 1; i < hi; i++) {
-                v += (uint32_t)(int32_t)delta[i];
-                out[i] = v;
-            }
-        }
-    };
+    auto work = [=](uint64_t b0, uint64_t b1) { mz::delta_decode_blocks(delta, base, n, b0, b1, out); };
     if (nt == 1) {
         work(0, nblk);
         return;
@@ -511,7 +506,7 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
     static const uint64_t delta_max_dev = getenv("MZ_DELTA_MAX_DEVICES") ? strtoull(getenv("MZ_DELTA_MAX_DEVICES"), nullptr, 10) : 2;
     const bool delta = p.mode == MZ_MODE_MINIMIZER && p.w <= 127 && !am.bits && !getenv("MZ_NO_POS_DELTA") && ND <= delta_max_dev;
     // host threads per decode / copy-out job: the jobs of all devices run side by side
-    const unsigned job_threads = std::max(2u, host_threads() / (unsigned)std::min<uint64_t>(ND, 4));
+    const unsigned job_threads = std::min(8u, std::max(2u, host_threads() / (unsigned)std::min<uint64_t>(ND, 4)));
     std::vector<Job> jobs(nchunks);
     uint64_t total = 0;
     bool too_small = false;
