@@ -155,6 +155,12 @@ struct DevState {
     PinBuf st_offs;                               // batch: chunk-local CSR offsets on their way out
     DevBuf<uint8_t> delta;                        // delta-coded pos / sk of a chunk (transfer codec)
     PinBuf st_delta;
+    // front-loaded uploads of the chunk pipelines (slot 0 of a device only): the device's whole
+    // share of the input, copied on its own stream as early as the link allows
+    DevBuf<uint8_t> in_all;
+    cudaStream_t up = nullptr;
+    cudaEvent_t up_t0 = nullptr, up_t1 = nullptr;
+    std::vector<cudaEvent_t> up_ev;  // one per chunk, grown on demand
 };
 
 }  // namespace
@@ -345,6 +351,17 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
     return MZ_OK;
 }
 
+// the n-th upload-done event of a device (created on first use, kept for the context's lifetime)
+int upload_event(DevState& d0, size_t n, cudaEvent_t* ev) {
+    while (d0.up_ev.size() <= n) {
+        cudaEvent_t e = nullptr;
+        CK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        d0.up_ev.push_back(e);
+    }
+    *ev = d0.up_ev[n];
+    return MZ_OK;
+}
+
 uint64_t estimate_capacity(const mz_params& p, uint64_t nwin) {
     double dens;
     if (p.mode == MZ_MODE_MINIMIZER) dens = 2.0 / (p.w + 1.0);
@@ -358,6 +375,9 @@ cudaError_t init_devstate(DevState& d, int device) {
     d.device = device;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreate(&d.up_t0);
+    if (e == cudaSuccess) e = cudaEventCreate(&d.up_t1);
     for (int j = 0; j < 5 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable | cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&d.hs_dev, d.hs, 0);
@@ -495,6 +515,8 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
         size_t nbytes, anbytes = 0;
         bool staged = false;
         float decode_ms = 0;
+        const uint8_t* d_in = nullptr;  // this chunk's bytes on its device
+        cudaEvent_t up_done = nullptr;  // front-loaded upload: the copy of this chunk has landed
     };
     // Pageable caller memory goes through pinned bounce buffers + multi-threaded memcpy; pinned
     // (mz_host_alloc / cudaHostRegister'ed) memory is used directly.
@@ -536,25 +558,66 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
             for (size_t i = 0; i < ndev; i++)
                 for (int sl = 0; sl < kSlots; sl++) {
                     DevState& d = ctx->slot(i, sl);
-                    if (cudaSetDevice(d.device) == cudaSuccess) cudaStreamSynchronize(d.stream);
+                    if (cudaSetDevice(d.device) == cudaSuccess) {
+                        cudaStreamSynchronize(d.stream);
+                        if (sl == 0) cudaStreamSynchronize(d.up);
+                    }
                 }
             cudaGetLastError();
             cudaSetDevice(ctx->devs[0].device);
         }
     } sync_all{ctx, ndev};
 
-    auto issue = [&](uint64_t c) -> int {
-        DevState& d = ctx->slot(dev_of(c), slot_of(c));
+    // geometry of every chunk
+    for (uint64_t c = 0; c < nchunks; c++) {
         Job& j = jobs[c];
-        CK(cudaSetDevice(d.device));
         j.wb = c * chunk;
         j.we = std::min<uint64_t>(j.wb + chunk, nwin);
         j.cap = estimate_capacity(p, j.we - j.wb);
         const uint64_t blo = j.wb > 0 ? j.wb - 1 : 0;
         j.byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
         j.nbytes = (bp_offset + j.we + l - 1 + 3) / 4 - j.byte_lo;
+    }
+    // Front-loaded uploads (pinned callers): a copy that runs while the other direction is busy
+    // slows both down (measured: 55 GB/s one way, 44 + 44 GB/s both ways), and the outputs are
+    // 3-5x the input.  So the whole input goes up first, on a stream of its own, as fast as the
+    // link takes it; the kernels wait for their chunk's event, and most of the D2H traffic then has
+    // the link to itself.  (Pageable input is staged chunk by chunk by the calling thread instead.)
+    const bool front = !page_in && !getenv("MZ_NO_FRONT_UPLOAD");
+    if (front) {
+        std::vector<size_t> share(ND, 0);
+        for (uint64_t c = 0; c < nchunks; c++) share[dev_of(c)] += (jobs[c].nbytes + 64 + 255) & ~size_t(255);
+        for (size_t i = 0; i < ndev; i++) {
+            CK(cudaSetDevice(ctx->devs[i].device));
+            if ((rc = ctx->devs[i].in_all.reserve(share[i] + 256))) return rc;
+            CK(cudaEventRecord(ctx->devs[i].up_t0, ctx->devs[i].up));
+        }
+        std::vector<size_t> off(ND, 0), nth(ND, 0);
+        for (uint64_t c = 0; c < nchunks; c++) {
+            const size_t di = dev_of(c);
+            DevState& d0 = ctx->devs[di];
+            Job& j = jobs[c];
+            CK(cudaSetDevice(d0.device));
+            uint8_t* dst = d0.in_all.p + off[di];
+            off[di] += (j.nbytes + 64 + 255) & ~size_t(255);
+            CK(cudaMemcpyAsync(dst, packed + j.byte_lo, j.nbytes, cudaMemcpyHostToDevice, d0.up));
+            if ((rc = upload_event(d0, nth[di]++, &j.up_done))) return rc;
+            CK(cudaEventRecord(j.up_done, d0.up));
+            j.d_in = dst;
+        }
+        for (size_t i = 0; i < ndev; i++) {
+            CK(cudaSetDevice(ctx->devs[i].device));
+            CK(cudaEventRecord(ctx->devs[i].up_t1, ctx->devs[i].up));
+        }
+    }
+
+    auto issue = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
+        Job& j = jobs[c];
+        CK(cudaSetDevice(d.device));
+        const uint64_t blo = j.wb > 0 ? j.wb - 1 : 0;
         int r;
-        if ((r = d.in.reserve(j.nbytes + 64))) return r;
+        if (!front && (r = d.in.reserve(j.nbytes + 64))) return r;
         if ((r = d.pos.reserve(j.cap))) return r;
         if (p.want_sk && (r = d.sk.reserve(j.cap))) return r;
         if (vw && (r = d.val.reserve(j.cap * vw))) return r;
@@ -565,11 +628,16 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
             src = d.st_in.p;
         }
         CK(cudaEventRecord(d.ev[0], d.stream));
-        CK(cudaMemcpyAsync(d.in.p, src, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+        if (front) {
+            CK(cudaStreamWaitEvent(d.stream, j.up_done, 0));
+        } else {
+            CK(cudaMemcpyAsync(d.in.p, src, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+            j.d_in = d.in.p;
+        }
         if (am.bits && (r = upload_amb(d, am, blo, j.we + l - 1, &j.abyte_lo, &j.anbytes))) return r;
         CK(cudaEventRecord(d.ev[1], d.stream));
         mz::KArgs a{};
-        fill_input_args(a, p, d.in.p, bp_offset, j.byte_lo, j.nbytes, nwin);
+        fill_input_args(a, p, j.d_in, bp_offset, j.byte_lo, j.nbytes, nwin);
         if (am.bits) fill_amb_args(a, am, d.amb.p, j.abyte_lo, j.anbytes);
         a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
         if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
@@ -653,7 +721,7 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
             if (p.want_sk && (r = d.sk.reserve(j.cap))) return r;
             if (vw && (r = d.val.reserve(j.cap * vw))) return r;
             mz::KArgs a{};
-            fill_input_args(a, p, d.in.p, bp_offset, j.byte_lo, j.nbytes, nwin);
+            fill_input_args(a, p, j.d_in, bp_offset, j.byte_lo, j.nbytes, nwin);
             if (am.bits) fill_amb_args(a, am, d.amb.p, j.abyte_lo, j.anbytes);
             a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
             if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
@@ -727,6 +795,12 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
     for (size_t hi = 0; hi < nhelp; hi++)
         if (int r = join_helper(hi)) return r;
     for (size_t hi = 0; hi < nhelp; hi++) collect_d2h(hi / kSlots, (int)(hi % kSlots));
+    if (front)
+        for (size_t i = 0; i < ndev; i++) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, ctx->devs[i].up_t0, ctx->devs[i].up_t1) == cudaSuccess) dev_h2d[i] = ms;
+            else cudaGetLastError();
+        }
     for (size_t i = 0; i < ndev; i++) {  // per-phase times: the busiest device
         ctx->timing.h2d_ms = std::max(ctx->timing.h2d_ms, dev_h2d[i]);
         ctx->timing.kernel_ms = std::max(ctx->timing.kernel_ms, dev_ker[i]);
@@ -992,6 +1066,12 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         d.offs.release(), d.rstart.release(), d.rlen.release(), d.pread.release(), d.pwin.release();
         d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release(), d.st_amb.release(), d.st_offs.release(), d.st_delta.release(), d.delta.release();
         d.amb.release();
+        d.in_all.release();
+        for (auto& e : d.up_ev)
+            if (e) cudaEventDestroy(e);
+        if (d.up_t0) cudaEventDestroy(d.up_t0);
+        if (d.up_t1) cudaEventDestroy(d.up_t1);
+        if (d.up) cudaStreamDestroy(d.up);
         for (auto& e : d.ev)
             if (e) cudaEventDestroy(e);
         if (d.hs) cudaFreeHost(d.hs);
@@ -1491,7 +1571,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             for (size_t i = 0; i < ctx->devs.size(); i++)
                 for (int sl = 0; sl < kSlots; sl++) {
                     DevState& d = ctx->slot(i, sl);
-                    if (cudaSetDevice(d.device) == cudaSuccess) cudaStreamSynchronize(d.stream);
+                    if (cudaSetDevice(d.device) == cudaSuccess) {
+                        cudaStreamSynchronize(d.stream);
+                        if (sl == 0) cudaStreamSynchronize(d.up);
+                    }
                 }
             cudaGetLastError();
             cudaSetDevice(ctx->devs[0].device);
@@ -1546,6 +1629,8 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         mz::KArgs a{};
         bool staged = false;
         std::vector<uint32_t> piece_read, piece_win0;
+        const uint8_t* d_in = nullptr;
+        cudaEvent_t up_done = nullptr;
     };
     std::vector<BJob> jobs(nchunks);
     uint64_t total = 0;
@@ -1585,6 +1670,43 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         if (hs_by_copy()) CK(cudaMemcpyAsync(d.hs, d.scratch.p, sizeof(HostScalars), cudaMemcpyDeviceToHost, d.stream));
         return MZ_OK;
     };
+
+    // Fixed-stride reads from pinned memory: the whole input goes up first on a stream of its own
+    // (see run_pipelined: copies in both directions at once slow each other down, and the output is
+    // 2-3x the input), every chunk's kernel waits for its own piece.
+    const bool front = !read_start_bp && !page_in && !getenv("MZ_NO_FRONT_UPLOAD");
+    if (front) {
+        std::vector<size_t> share(ND, 0), off(ND, 0), nth(ND, 0);
+        auto span = [&](uint64_t c, uint64_t* lo, size_t* nb) {
+            const uint64_t r0 = c * chunk_reads, r1 = std::min<uint64_t>(r0 + chunk_reads, n_reads);
+            *lo = (r0 * stride_bytes) & ~uint64_t(3);
+            *nb = (size_t)((r1 - 1) * stride_bytes + (fixed_len_bp + 3) / 4 - *lo);
+        };
+        for (uint64_t c = 0; c < nchunks; c++) {
+            uint64_t lo;
+            size_t nb;
+            span(c, &lo, &nb);
+            share[dev_of(c)] += (nb + 64 + 255) & ~size_t(255);
+        }
+        for (size_t i = 0; i < ND; i++) {
+            CK(cudaSetDevice(ctx->devs[i].device));
+            if ((rc = ctx->devs[i].in_all.reserve(share[i] + 256))) return rc;
+        }
+        for (uint64_t c = 0; c < nchunks; c++) {
+            const size_t di = dev_of(c);
+            DevState& d0 = ctx->devs[di];
+            uint64_t lo;
+            size_t nb;
+            span(c, &lo, &nb);
+            CK(cudaSetDevice(d0.device));
+            uint8_t* dst = d0.in_all.p + off[di];
+            off[di] += (nb + 64 + 255) & ~size_t(255);
+            CK(cudaMemcpyAsync(dst, packed + lo, nb, cudaMemcpyHostToDevice, d0.up));
+            if ((rc = upload_event(d0, nth[di]++, &jobs[c].up_done))) return rc;
+            CK(cudaEventRecord(jobs[c].up_done, d0.up));
+            jobs[c].d_in = dst;
+        }
+    }
 
     auto issue = [&](uint64_t c) -> int {
         DevState& d = ctx->slot(dev_of(c), slot_of(c));
@@ -1646,7 +1768,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             j.grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * std::max<size_t>(1, std::min<size_t>(8, (220 * 1024) / (j.smem + 1024))));
         }
         j.cap = std::min<uint64_t>(estimate_capacity(*p, j.windows) + nr, std::max<uint64_t>(j.windows, 1));
-        if ((r = d.in.reserve(j.nbytes + 64))) return r;
+        if (!front && (r = d.in.reserve(j.nbytes + 64))) return r;
         if ((r = d.offs.reserve(nr + 1))) return r;
         if (read_start_bp) {
             if ((r = d.rstart.reserve(nr))) return r;
@@ -1663,7 +1785,12 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
             src = d.st_in.p;
         }
         CK(cudaEventRecord(d.ev[0], d.stream));
-        CK(cudaMemcpyAsync(d.in.p, src, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+        if (front) {
+            CK(cudaStreamWaitEvent(d.stream, j.up_done, 0));
+        } else {
+            CK(cudaMemcpyAsync(d.in.p, src, j.nbytes, cudaMemcpyHostToDevice, d.stream));
+            j.d_in = d.in.p;
+        }
         if (pieces) {
             CK(cudaMemcpyAsync(d.pread.p, j.piece_read.data(), j.n_units * 4, cudaMemcpyHostToDevice, d.stream));
             CK(cudaMemcpyAsync(d.pwin.p, j.piece_win0.data(), j.n_units * 4, cudaMemcpyHostToDevice, d.stream));
@@ -1675,7 +1802,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         CK(cudaEventRecord(d.ev[1], d.stream));
         mz::KArgs& a = j.a;
         fill_hash_args(a, *p);
-        a.seq = reinterpret_cast<const uint32_t*>(d.in.p);
+        a.seq = reinterpret_cast<const uint32_t*>(j.d_in);
         // ragged reads keep their absolute start positions; fixed-stride reads are chunk-local
         a.bitbias = read_start_bp ? -(int64_t)(8 * j.byte_lo) : (int64_t)(8 * (lo - j.byte_lo));
         a.seq_nwords = (j.nbytes + 3) / 4;
