@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmzb200.so")
+# MZ_B200_LIB: another build of the same library (A/B experiments with compile-time variants)
+LIB_PATH = os.environ.get("MZ_B200_LIB") or os.path.join(_PKG, "libmzb200.so")
 
 MZ_OK = 0
 ERR_NAMES = {

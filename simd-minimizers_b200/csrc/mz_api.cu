@@ -316,9 +316,7 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
         pl.num_tiles = fp.num_tiles;
         if ((rc = d.rows.reserve((fp.scratch_words_per_block * 2 + fp.r1_words) * fp.grid * mz::FAST_WARPS))) return rc;
         a.scratch = d.rows.p;
-        a.scratch_words_per_block = fp.scratch_words_per_block;
-        a.r1_words_per_warp = fp.r1_words;
-        a.list_cap = fp.list_cap;
+        mz::fast_plan_args(fp, a);
     } else {
         rc = plan_generic(d, p, wend - wbeg, &pl);
         a.scratch = nullptr;
@@ -1589,8 +1587,11 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     const bool fast = p->w <= mz::FAST_MAX_W || (p->w <= mz::FAST_XW_MAX_W && !getenv("MZ_NO_XW"));
     uint32_t S_cap, NTg = 128;
     if (fast) {
-        S_cap = 288;
-        while (S_cap > 16 && mz::fast_smem(S_cap, p->w, mz::fast_list_cap(S_cap, *p)) > mz::FAST_SMEM_LIMIT) S_cap -= 16;
+        // thread = read (or piece of a read): as many windows per thread as the queues hold
+        mz::FastPlan probe;
+        S_cap = 512;
+        while (S_cap > 16 && !mz::fast_queue_plan(S_cap, *p, &probe)) S_cap -= 16;
+        if (!mz::fast_queue_plan(S_cap, *p, &probe)) S_cap = 1;
     } else {
         const size_t budget = std::min<size_t>(ctx->devs[0].smem_optin, 200 * 1024);
         while (NTg >= 32 && generic_smem(NTg, 32, p->w, lr) > budget) NTg /= 2;
@@ -1653,9 +1654,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         if (fast) {
             if ((r = d.rows.reserve((j.fp.scratch_words_per_block * 2 + j.fp.r1_words) * j.fp.grid * mz::FAST_WARPS))) return r;
             a.scratch = d.rows.p;
-            a.scratch_words_per_block = j.fp.scratch_words_per_block;
-            a.r1_words_per_warp = j.fp.r1_words;
-            a.list_cap = j.fp.list_cap;
+            mz::fast_plan_args(j.fp, a);
             r = mz::launch_fast(*p, j.fp.grid, a, d.stream);
         } else {
             Plan pl;
@@ -1753,12 +1752,9 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         if (fast) {
             const uint64_t tiles = (j.n_units + 31) / 32;
             if (tiles > 0x7fffffffull) return MZ_ERR_UNSUPPORTED;
-            j.fp.S = S;
+            if (!mz::fast_queue_plan(S, *p, &j.fp)) return MZ_ERR_UNSUPPORTED;
             j.fp.num_tiles = (uint32_t)tiles;
             j.fp.grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)d.sm_count * mz::FAST_BPS);
-            j.fp.scratch_words_per_block = mz::fast_scratch_words(S, p->w);
-            j.fp.r1_words = mz::fast_r1_words(S, p->w, lr);
-            j.fp.list_cap = mz::fast_list_cap(S, *p);
             j.num_tiles = j.fp.num_tiles;
         } else {
             const uint64_t tiles = (j.n_units + NTg - 1) / NTg;

@@ -41,8 +41,14 @@ struct KArgs {
     uint32_t num_tiles;
     uint32_t* scratch;                 // fast kernel: per-warp record rows (L2-resident); generic: global ring
     uint64_t scratch_words_per_block;  // fast kernel: words per WARP and buffer; generic: per block
-    uint32_t list_cap;                 // fast kernel: staging entries per warp and pass
+    uint32_t list_cap;                 // (generic kernel only)
     uint64_t r1_words_per_warp;        // fast kernel, w > 32: level-1 result rows per warp (else 0)
+    // fast kernel: per-lane emission queues in shared memory (rows of 32 entries, one per lane)
+    uint32_t q_rows;                   // rows per warp and buffer (q_trig + one loop iteration of guard rows)
+    uint32_t q_trig;                   // a lane holding more rows than this at the end of an iteration spills the warp's queues
+    uint32_t nb;                       // loop iterations per tile (the same for every lane)
+    uint32_t lead;                     // elements in front of the first valid window end
+    uint32_t one;                      // always 1 (see mz_fast.cuh: keeps additions on the FMA pipe)
     // batch mode (thread per read); reads == 0 -> single sequence
     uint64_t n_reads;
     const uint64_t* read_start_bp;   // may be null -> fixed stride
@@ -82,22 +88,23 @@ __device__ __forceinline__ uint32_t ld_bits32(const KArgs& a, uint64_t bit) {
 }
 
 // ---- ambiguity mask (one bit per base) -------------------------------------------------------
-__device__ __forceinline__ uint32_t amb_word(const KArgs& a, uint64_t wi) {
-    return wi < a.amb_nwords ? __ldg(a.amb + wi) : 0u;
+// (bits in front of / behind the mask read as 0 = unambiguous)
+__device__ __forceinline__ uint32_t amb_word(const KArgs& a, int64_t wi) {
+    return (wi >= 0 && (uint64_t)wi < a.amb_nwords) ? __ldg(a.amb + wi) : 0u;
 }
-// 32 mask bits starting at bit index `bit`
-__device__ __forceinline__ uint32_t amb_bits32(const KArgs& a, uint64_t bit) {
-    const uint64_t wi = bit >> 5;
+// 32 mask bits starting at bit index `bit` (may be negative)
+__device__ __forceinline__ uint32_t amb_bits32(const KArgs& a, int64_t bit) {
+    const int64_t wi = bit >> 5;
     return __funnelshift_r(amb_word(a, wi), amb_word(a, wi + 1), (uint32_t)bit & 31u);
 }
 // any ambiguous base among the n bases starting at mask bit `bit`?
-static __device__ __noinline__ bool amb_any(const KArgs& a, uint64_t bit, uint32_t n) {
+static __device__ __noinline__ bool amb_any(const KArgs& a, int64_t bit, uint32_t n) {
     for (; n >= 32; n -= 32, bit += 32)
         if (amb_bits32(a, bit)) return true;
     return n != 0 && (amb_bits32(a, bit) & ((1u << n) - 1u)) != 0;
 }
 // number of unambiguous bases at the end of the n bases starting at mask bit `bit`
-static __device__ __noinline__ uint32_t amb_clean_run(const KArgs& a, uint64_t bit, uint32_t n) {
+static __device__ __noinline__ uint32_t amb_clean_run(const KArgs& a, int64_t bit, uint32_t n) {
     uint32_t run = 0;
     for (uint32_t i = 0; i < n; i += 32) {
         const uint32_t m = amb_bits32(a, bit + i), take = n - i < 32u ? n - i : 32u;
@@ -108,7 +115,7 @@ static __device__ __noinline__ uint32_t amb_clean_run(const KArgs& a, uint64_t b
 // One loop iteration of the fast kernel: bit t of .x <=> the l bases ending at mask bit
 // `bit + t` are all unambiguous (t < n <= 32); `run` = clean run ending just before `bit`,
 // .y = the run after the n bases.
-static __device__ __noinline__ uint2 amb_clean_mask(const KArgs& a, uint64_t bit, uint32_t n, uint32_t l,
+static __device__ __noinline__ uint2 amb_clean_mask(const KArgs& a, int64_t bit, uint32_t n, uint32_t l,
                                                     uint32_t run) {
     const uint32_t m = amb_bits32(a, bit);
     uint32_t clean = 0;

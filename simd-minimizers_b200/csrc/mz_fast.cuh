@@ -1,7 +1,7 @@
 // mz_fast.cuh -- W-specialised, register-resident minimizer / syncmer kernel for sm_100a.
 //
 // Persistent warps pull tiles (32 threads x S windows) from a ticket counter; every warp is an
-// autonomous worker (own look-back, own staging), so there is no block barrier after start-up.
+// autonomous worker (own look-back, own queues), so there is no block barrier after start-up.
 // One thread walks S consecutive windows.  Per van-Herk block of W k-mers (fully unrolled):
 //   * the words holding the entering- and leaving-base streams were prefetched one block ahead;
 //     they are re-aligned with funnel shifts and interleaved so that every byte holds
@@ -12,16 +12,22 @@
 //   * (hash & 0xffff0000) | pos goes through a prefix-min / suffix-min pair whose W-entry suffix
 //     array lives in registers (static indexing); the rightmost minimum uses max on the
 //     complemented key, exactly the reference's packing (src/sliding_min.rs:190-195,336-341);
-//   * leftmost != rightmost is detected once per iteration from the packed position bytes of
-//     the two chains (one LOP3 per four windows); the strand rule
-//     (src/canonical.rs) runs in a cold fix-up for the few blocks that contain such a window;
-//   * the low byte of the selected position and a flag bit per window go to an L2-resident
-//     global scratch (coalesced rows); the warp then turns them into ordered, coalesced output
-//     (look-back over tile descriptors, staging list, software-pipelined emission pass).
+//   * leftmost != rightmost (1.2e-4 of windows) is tested per pair of windows with two LOP3; the
+//     strand rule (src/canonical.rs) runs out of line for those windows only;
+//   * a window whose selection differs from the previous window's (src/collect.rs:39-76) pushes ONE
+//     16-bit entry -- (selected k-mer << 5 | distance to the window end), built by a single IMAD --
+//     onto the lane's queue in shared memory with a predicated store: nothing is recorded for the
+//     nine windows in ten that emit nothing, and nothing is re-read or re-walked afterwards.
+// The warp then turns its 32 queues into ordered, coalesced output: warp scan of the lane counts,
+// decoupled look-back over tile descriptors (resolved one tile later, so predecessors have
+// published), and one software-pipelined pass in which lane x & 31 handles output entry x (owner
+// lane found by walking the 33 lane offsets, k-mer words fetched one entry ahead).
 #pragma once
 #include "../../include/mz_b200.h"
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
+#include <type_traits>
 #include "mz_emit.cuh"
 
 namespace mz {
@@ -29,23 +35,23 @@ namespace mz {
 constexpr uint32_t FAST_MAX_W = 32;
 // One block of 16 autonomous warps per SM.  (Warps never synchronise after start-up, so the block
 // size only decides how many warps share one copy of the hash table in shared memory.)
-constexpr uint32_t FAST_NT = 512;   // threads per block
+#ifndef MZ_FAST_NT
+#define MZ_FAST_NT 512
+#endif
+constexpr uint32_t FAST_NT = MZ_FAST_NT;   // threads per block
 constexpr uint32_t FAST_BPS = 1;    // resident blocks per SM
 // The 256-entry delta table is stored FAST_TC times, copy c = lane & 7 interleaved so that entry
 // e of copy c sits at 16-byte slot e*8 + c: the eight lanes of a quarter warp (one LDS.128 pass)
 // always hit eight different bank groups -> no bank conflicts on the random table lookups.
 constexpr uint32_t FAST_TC = 8;
-constexpr size_t FAST_SMEM_LIMIT = 194 * 1024;  // per block (196 KB carve-out): ~60 KB of L1 stay for the input stream
+constexpr size_t FAST_SMEM_LIMIT = 204 * 1024;  // per block: ~50 KB of L1 stay for the input stream
+constexpr uint32_t FAST_WARPS = FAST_NT / 32;
+constexpr uint32_t FAST_TOFFS = 36;  // words per warp and buffer: 33 lane offsets (+ padding)
 
-// Per-block scratch in GLOBAL memory (L2-resident: a few hundred KB per resident block, reused
-// for every tile the persistent block processes).  Row r, thread t -> word scratch[r*NT + t]:
-//   rows (b*WQ + q)   low bytes of the selected positions of windows 4q..4q+3 of van-Herk block b
-// The flag word of block b (bit t <-> window ending at element bW+t) stays in shared memory.
 // Small windows: several van-Herk blocks (B of them, B*W <= 32 k-mers) share one loop iteration, so
-// the per-iteration ingest/record overhead is amortised over ~32 k-mers for every W.
+// the per-iteration ingest overhead is amortised over ~32 k-mers for every W.
 __host__ __device__ constexpr uint32_t fast_b(uint32_t W) { return W <= 16 ? 32 / W : 1; }
 __host__ __device__ constexpr uint32_t fast_sb(uint32_t W) { return fast_b(W) * W; }
-__host__ __device__ constexpr uint32_t fast_wq(uint32_t W) { return (fast_sb(W) + 3) / 4; }
 // Windows longer than FAST_MAX_W (XW instances): the minimum over w k-mers is the minimum over
 // T+1 shifted sub-windows of wt = fast_wt(w) <= 24 k-mers each; the kernel instance is the one of
 // wt.  For w <= FAST_MAX_W, wt = w.
@@ -55,14 +61,21 @@ __host__ __device__ inline uint32_t fast_wt(uint32_t w) {
     const uint32_t parts = (w + 23) / 24;
     return (w + parts - 1) / parts;
 }
+// Elements (k-mers) a thread computes in front of its first valid window end: the w k-mers of the
+// window in front of its segment (whose result only seeds the dedup comparison -- the reference's
+// lane-seam rule, src/collect.rs:252-272), rounded up to whole van-Herk blocks so that the
+// lead-in ends on a block boundary and everything it pushed is dropped by resetting the queue.
+__host__ __device__ inline uint32_t fast_lead(uint32_t w) {
+    const uint32_t wt = fast_wt(w);
+    return (w + wt - 1) / wt * wt;
+}
 __host__ __device__ inline uint32_t fast_nb(uint32_t S, uint32_t w) {
     const uint32_t sb = fast_sb(fast_wt(w));
-    return (S + 1 + (w - 1) + sb - 1) / sb;  // k-mers = S + has_prev + w - 1
+    return (fast_lead(w) + S + sb - 1) / sb;
 }
-// scratch words per WARP (a warp is an autonomous worker: tile = 32 threads x S windows)
-inline size_t fast_scratch_words(uint32_t S, uint32_t w) {
-    return (size_t)fast_nb(S, w) * fast_wq(fast_wt(w)) * 32;
-}
+// queue entry: u16 = selected k-mer (11 bits, lane-local) << 5 | window end - selected k-mer;
+// long windows need 8 bits for the distance and use u32 entries
+__host__ __device__ inline uint32_t fast_qbytes(uint32_t w) { return w > FAST_MAX_W ? 4u : 2u; }
 // XW instances: words per warp for the ring of level-1 results (one row of 32 lanes per k-mer;
 // leftmost and rightmost sub-window minimum for strand-aware builders)
 __host__ __device__ inline uint32_t fast_ring_rows(uint32_t w) {  // power of two >= (w - wt) + iteration
@@ -71,45 +84,71 @@ __host__ __device__ inline uint32_t fast_ring_rows(uint32_t w) {  // power of tw
     while (r < need) r <<= 1;
     return r;
 }
-inline size_t fast_r1_words(uint32_t S, uint32_t w, bool lr) {
-    (void)S;
+inline size_t fast_r1_words(uint32_t w, bool lr) {
     return w <= FAST_MAX_W ? 0 : (size_t)fast_ring_rows(w) * 32 * (lr ? 2 : 1);
 }
-constexpr uint32_t FAST_WARPS = FAST_NT / 32;
-// shared memory: table | misc | per-warp staging list | per-warp flag words (2 tiles in flight)
-inline size_t fast_smem(uint32_t S, uint32_t W, uint32_t list_cap) {
-    return 256 * FAST_TC * 16 + 32 + (size_t)FAST_WARPS * list_cap * 4 + (size_t)FAST_WARPS * 2 * fast_nb(S, W) * 32 * 4;
+// Global spill area, words per WARP and buffer: every entry a lane can push in one tile.  Only
+// touched when a lane's queue overflows (low-complexity sequence: far more minimizers than the
+// random-sequence density the queues are sized for).
+inline size_t fast_spill_words(uint32_t S, uint32_t w) {
+    return (size_t)fast_nb(S, w) * fast_sb(fast_wt(w)) * 32 * fast_qbytes(w) / 4;
 }
-// staging entries per warp: 1.5x the expected emissions of a tile (a second pass handles more)
-inline uint32_t fast_list_cap(uint32_t S, const mz_params& p) {
-    const double dens = p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
-                      : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
-    static const double slack = getenv("MZ_FAST_LISTF") ? atof(getenv("MZ_FAST_LISTF")) : 1.5;
-    const uint32_t want = (uint32_t)(32.0 * S * dens * slack) + 64;
-    // ... but never more than what keeps the block within FAST_SMEM_LIMIT: dense outputs
-    // (small w) simply take more staging passes per tile
-    const size_t fixed = fast_smem(S, p.w, 0);
-    const uint32_t fit = fixed + 256 * 4 * FAST_WARPS >= FAST_SMEM_LIMIT
-                             ? 256u : (uint32_t)((FAST_SMEM_LIMIT - fixed) / (4 * FAST_WARPS)) / 128 * 128;
-    return std::max<uint32_t>(std::min<uint32_t>((want + 127) / 128 * 128, std::min<uint32_t>(fit, 4096)), 256);
+// shared memory: table | misc | per warp: lane offsets (2 tiles in flight) | queues (2 tiles in flight)
+inline size_t fast_smem(uint32_t w, uint32_t q_rows) {
+    return 256 * FAST_TC * 16 + 64 +
+           (size_t)FAST_WARPS * (2 * FAST_TOFFS * 4 + 2 * (size_t)q_rows * 32 * fast_qbytes(w));
+}
+inline double fast_density(const mz_params& p) {
+    return p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
+         : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
+}
+// rows a lane may hold before the warp spills: expected entries of a segment + 6 sigma-ish slack
+inline uint32_t fast_q_trig(uint32_t S, const mz_params& p) {
+    // (the number of minimizers in S windows has a standard deviation of about sqrt(2 S / 3 w):
+    // gaps are close to uniform on 1..w; syncmers: Poisson-like)
+    static const double nsig = getenv("MZ_FAST_QSIGMA") ? atof(getenv("MZ_FAST_QSIGMA")) : 6.0;
+    const double mean = S * fast_density(p);
+    const double sigma = p.mode == MZ_MODE_MINIMIZER ? sqrt(2.0 * S / (3.0 * p.w)) : sqrt(mean);
+    return (uint32_t)std::min<double>(S + 1.0, mean + nsig * sigma + 4.0);
+}
+
+// Word `widx` of the packed stream, any index: 0 in front of the buffer, clamped behind it
+// (bases outside the sequence only ever feed windows that are discarded).
+__device__ __forceinline__ uint32_t ld_word_any(const uint32_t* seq, uint64_t nwords, int64_t widx) {
+    if (widx < 0) return 0u;
+    return __ldg(seq + ((uint64_t)widx < nwords ? (uint64_t)widx : nwords - 1));
 }
 
 // Rare path (leftmost != rightmost minimum): strand rule 2*#TG > l on the window's l bases
 // (src/canonical.rs:19-29).  Kept out of line so the unrolled hot loop stays small.
-static __device__ __noinline__ bool window_prefers_left(const uint32_t* wbase, uint32_t sh0, uint32_t wlim,
-                                                 uint32_t lbit, uint32_t l) {
-    uint32_t p = sh0 + lbit, bits = 2u * l, cnt = 0;
+static __device__ __noinline__ bool window_prefers_left(const uint32_t* seq, uint64_t nwords, int64_t bit, uint32_t l) {
+    uint32_t bits = 2u * l, cnt = 0;
     while (bits) {
-        const uint32_t wl = p >> 5, sh = p & 31u;
-        const uint32_t w0 = __ldg(wbase + min(wl, wlim)), w1 = __ldg(wbase + min(wl + 1, wlim));
-        uint32_t v = __funnelshift_r(w0, w1, sh) & 0xAAAAAAAAu;
+        const int64_t wl = bit >> 5;
+        const uint32_t sh = (uint32_t)bit & 31u;
+        uint32_t v = __funnelshift_r(ld_word_any(seq, nwords, wl), ld_word_any(seq, nwords, wl + 1), sh) & 0xAAAAAAAAu;
         const uint32_t take = bits < 32u ? bits : 32u;
         if (take < 32u) v &= (1u << take) - 1u;
         cnt += __popc(v);
-        p += take;
+        bit += take;
         bits -= take;
     }
     return 2u * cnt > l;
+}
+
+// Selections of up to four consecutive windows (the last k-mer of the first one is local element
+// `pos`) whose leftmost (r) and rightmost (m, complemented key) minimum may differ; bit0 = bit
+// position of local base 0.  One call per group of four: the hot loop only carries the call.
+static __device__ __noinline__ uint4 tie_fix4(const KArgs& a, int64_t bit0, uint32_t pos, uint32_t ng, uint4 r, uint4 m) {
+    uint32_t rr[4] = {r.x, r.y, r.z, r.w};
+    const uint32_t mm[4] = {m.x, m.y, m.z, m.w};
+#pragma unroll
+    for (uint32_t u = 0; u < 4; u++) {
+        if (u >= ng || ((rr[u] ^ mm[u]) & 0xffffu) == 0u) continue;
+        const int64_t wbit = bit0 + 2 * ((int64_t)(pos + u) - (int64_t)(a.w - 1u));
+        if (!window_prefers_left(a.seq, a.seq_nwords, wbit, a.l)) rr[u] = mm[u] ^ 0xffff0000u;
+    }
+    return make_uint4(rr[0], rr[1], rr[2], rr[3]);
 }
 
 __device__ __forceinline__ uint4 lds128(uint32_t addr) {
@@ -122,13 +161,8 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
     asm("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
     return v;
 }
-// bf |= bit when a != b (forced to SETP + predicated OR: two issue slots)
-__device__ __forceinline__ void or_if_ne(uint32_t& bf, uint32_t a, uint32_t b, uint32_t bit) {
-    asm("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p or.b32 %0, %0, %3;\n\t}" : "+r"(bf) : "r"(a), "r"(b), "r"(bit));
-}
-// a*b + c written as mad.lo in PTX, b = 1 from a volatile mov.  ptxas still picks the pipe per
-// use, but with plain C++ adds for the positions it allocates 128 instead of 115 registers and
-// the w = 31 instance runs 19 % slower (measured), so the positions stay expressed this way.
+// a*b + c written as mad.lo in PTX (b from a volatile mov when it is 1): the positions and the
+// queue entries are built on the FMA pipe, which idles while the ALU pipe is the busy one.
 __device__ __forceinline__ uint32_t imad(uint32_t a, uint32_t b, uint32_t c) {
     uint32_t d;
     asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -141,12 +175,262 @@ __device__ __forceinline__ T* pinned(T* p) {
     asm volatile("" : "+l"(p));
     return p;
 }
-// J is a compile-time constant after unrolling
-__device__ __forceinline__ uint32_t put_byte(uint32_t acc, uint32_t v, int J) {  // acc.byte[J] = v.byte[0]
-    return __byte_perm(acc, v, J == 0 ? 0x3214 : J == 1 ? 0x3240 : J == 2 ? 0x3410 : 0x4210);
-}
 __device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
     return J == 0 ? (w & 0xffu) : J == 3 ? (w >> 24) : __byte_perm(w, 0, 0x4440 + J);
+}
+
+// ---- per-lane emission queue (shared memory; qa = byte address of the lane's next row) -----------
+// push `ent` when a != b: SETP + predicated STS + predicated add, no branch
+template <int ROWB, bool WIDE>
+__device__ __forceinline__ void q_push_ne(uint32_t& qa, uint32_t a, uint32_t b, uint32_t ent) {
+    if constexpr (WIDE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p st.shared.u32 [%0], %3;\n\t@p add.u32 %0, %0, %4;\n\t}"
+                     : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "n"(ROWB));
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b16 lo;\n\tsetp.ne.u32 p, %1, %2;\n\tcvt.u16.u32 lo, %3;\n\t"
+                     "@p st.shared.u16 [%0], lo;\n\t@p add.u32 %0, %0, %4;\n\t}"
+                     : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "n"(ROWB));
+}
+// the same with the pointer bump as rowb * one + qa (FMA pipe; rowb holds ROWB, one holds 1)
+template <bool WIDE>
+__device__ __forceinline__ void q_push_ne_fma(uint32_t& qa, uint32_t a, uint32_t b, uint32_t ent, uint32_t rowb, uint32_t one) {
+    if constexpr (WIDE)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p st.shared.u32 [%0], %3;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t}"
+                     : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "r"(rowb), "r"(one));
+    else
+        asm volatile("{\n\t.reg .pred p;\n\t.reg .b16 lo;\n\tsetp.ne.u32 p, %1, %2;\n\tcvt.u16.u32 lo, %3;\n\t"
+                     "@p st.shared.u16 [%0], lo;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t}"
+                     : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "r"(rowb), "r"(one));
+}
+// entry at shared address `addr`
+template <bool WIDE>
+__device__ __forceinline__ uint32_t q_load(uint32_t addr) {
+    if constexpr (WIDE) {
+        uint32_t v;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+        return v;
+    } else {
+        uint16_t h;
+        asm volatile("ld.shared.u16 %0, [%1];" : "=h"(h) : "r"(addr));
+        return h;
+    }
+}
+// move n rows of a lane's queue (first row at shared address qa0) to its slice of the spill area
+template <int ROWB, bool WIDE, typename QT>
+static __device__ __noinline__ void q_spill(uint32_t qa0, uint32_t n, QT* dst) {
+    for (uint32_t i = 0; i < n; i++) dst[i] = (QT)q_load<WIDE>(qa0 + i * (uint32_t)ROWB);
+}
+template <int ROWB, bool WIDE>
+__device__ __forceinline__ void q_push_if(uint32_t& qa, bool c, uint32_t ent) {
+    q_push_ne<ROWB, WIDE>(qa, (uint32_t)c, 0u, ent);
+}
+
+// What one thread of a tile works on.  Local element e is the k-mer starting at base F + e, where
+// F = (first window of the segment) - 1 - (lead - w): every thread starts one window (plus block
+// padding for long windows) in front of its segment, so the first valid window ends at element
+// `lead` for every thread.  F is negative for the first thread of a sequence / a read: bases in
+// front of the buffer read as 'A' and only reach discarded windows.
+struct FSeg {
+    int64_t bit0;        // bit position (in a.seq, may be negative) of local base 0
+    uint32_t nvalid;     // windows this thread may emit
+    uint32_t first_always;  // no window in front of the segment: its first window always emits
+};
+__device__ __forceinline__ FSeg make_fseg(const KArgs& a, uint32_t tile, uint32_t lane) {
+    FSeg s;
+    const int64_t back = 1 + (int64_t)(a.lead - a.w);
+    if (a.n_reads == 0) {
+        const uint64_t j0 = a.wbeg + ((uint64_t)tile * 32u + lane) * a.S;
+        const uint64_t left = j0 < a.wend ? a.wend - j0 : 0;
+        s.nvalid = (uint32_t)(left < a.S ? left : a.S);
+        s.first_always = (j0 == 0);
+        s.bit0 = 2 * ((int64_t)j0 - back) + a.bitbias;
+    } else {
+        const uint64_t pi = (uint64_t)tile * 32u + lane;
+        s.nvalid = 0;
+        s.first_always = 1;
+        s.bit0 = a.bitbias;
+        if (pi < a.n_reads) {
+            const uint64_t r = a.piece_read ? a.piece_read[pi] : pi;
+            const uint32_t win0 = a.piece_read ? a.piece_win0[pi] : 0u;
+            const uint64_t startbits = a.read_start_bp ? 2 * a.read_start_bp[r] : r * a.stride_bits;
+            const uint32_t len = a.read_len_bp ? a.read_len_bp[r] : a.fixed_len_bp;
+            const uint32_t nw = len >= a.l ? len - a.l + 1 : 0;
+            const uint32_t left = nw > win0 ? nw - win0 : 0;
+            s.nvalid = left < a.S ? left : a.S;
+            s.first_always = (win0 == 0);
+            s.bit0 = (int64_t)startbits + 2 * ((int64_t)win0 - back) + a.bitbias;
+        }
+    }
+    return s;
+}
+
+// ---- ordered emission of one tile (called by a whole warp, once per tile) -------------------------
+// tp[t] = exclusive output offset of lane t inside the tile, tp[32] = the tile's total; entry i of
+// lane t lives at ebase + i * sI + t * sT (shared-memory queue rows, or the global spill area).
+// Lane x & 31 handles output entry x; the owner lane of x is found by walking the lane offsets
+// (x grows by 32 per step and a lane holds ~40 entries, so the walk advances by 0 or 1 almost always).
+
+// 2-bit reverse complement of the low 2*len bits of v (len <= 32), as 32-bit halves
+__device__ __forceinline__ uint64_t revcomp64(uint64_t v, uint32_t len) {
+    uint32_t lo = __brev((uint32_t)(v >> 32)), hi = __brev((uint32_t)v);  // bit reversal swaps the halves
+    // swap the two bits of every base and complement (code ^ 2): m ? (x >> 1) : ~(x << 1), m = 0x5555...
+    lo = ((lo >> 1) & 0x55555555u) | (~(lo << 1) & 0xAAAAAAAAu);
+    hi = ((hi >> 1) & 0x55555555u) | (~(hi << 1) & 0xAAAAAAAAu);
+    return (((uint64_t)hi << 32) | lo) >> (64 - 2 * len);
+}
+
+template <int VB, bool XW>
+__device__ __forceinline__ void fast_emit_seq(const KArgs& a, uint32_t tile, unsigned long long gbase, uint32_t total,
+                                              const uint32_t* tp, uint32_t qs) {
+    // qs = shared address of the tile's queue rows: entry i of lane t at qs + i * ROWB + t * sizeof(QT)
+    using QT = typename std::conditional<XW, uint32_t, uint16_t>::type;
+    constexpr uint32_t DBITS = XW ? 8 : 5, DMASK = (1u << DBITS) - 1u, ROWB = 32 * sizeof(QT);
+    constexpr int NW = VB == 64 ? 3 : VB == 128 ? 5 : 0;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t Wr = a.w, S = a.S, len = a.val_len;
+    const bool minim = a.mode == MODE_MINIMIZER, want_sk = a.want_sk != 0, canon_val = a.val_canonical != 0;
+    uint32_t* const opos = pinned(a.pos + gbase);
+    uint32_t* const osk = pinned(a.sk + (want_sk ? gbase : 0ull));
+    unsigned long long* const oval = pinned(reinterpret_cast<unsigned long long*>(a.val) + (VB ? gbase * (VB / 64) : 0ull));
+    // Tile-uniform addressing.  Lane t's local element 0 is the k-mer at position pos00 + t * S with
+    // pos00 = (first window of the tile) - 1 - (lead - w).
+    const uint64_t j00 = a.wbeg + (uint64_t)tile * 32u * S;
+    const int64_t back = 1 + (int64_t)(a.lead - Wr);
+    const uint32_t pos00 = (uint32_t)((int64_t)j00 - back);
+    const int64_t tbit0 = 2 * ((int64_t)j00 - back) + a.bitbias;
+    const uint32_t* const twbase = pinned(a.seq + (tbit0 >> 5));  // never dereferenced below word 0
+    const uint32_t tsh = (uint32_t)tbit0 & 31u;
+    const int64_t trem = (int64_t)a.seq_nwords - 1 - (tbit0 >> 5);
+    const uint32_t twlim = trem > 0x7ffffff0ll ? 0x7ffffff0u : (uint32_t)trem;  // last readable word
+    const uint32_t mlo = len < 16 ? (1u << (2 * len)) - 1u : 0xffffffffu;
+    const uint32_t mhi = len <= 16 ? 0u : len < 32 ? (1u << (2 * len - 32)) - 1u : 0xffffffffu;
+
+    struct Ent {
+        uint32_t rel, sk, w[NW ? NW : 1];
+    };
+    uint32_t t = 0, lo = 0, hi = tp[1];
+    // locate entry x, decode it, request the words of its k-mer
+    auto stageB = [&](uint32_t x, Ent& e) {
+        while (x >= hi) {  // 0 or 1 steps almost always (a lane holds more than 32 entries on average)
+            t++;
+            lo = hi;
+            hi = tp[t + 1];
+        }
+        const uint32_t v = q_load<XW>(qs + (x - lo) * ROWB + t * (uint32_t)sizeof(QT));
+        const uint32_t posl = v >> DBITS, wst = posl + (v & DMASK) - (Wr - 1u);  // selected k-mer, first k-mer of the window
+        const uint32_t base = t * S;
+        e.rel = base + (minim ? posl : wst);  // reported k-mer, counted from the tile's element 0
+        e.sk = pos00 + base + wst;            // = index of the window
+        if (NW) {
+            const uint32_t wl = (tsh + 2u * e.rel) >> 5;
+#pragma unroll
+            for (int q = 0; q < NW; q++) e.w[q] = __ldg(twbase + min(wl + q, twlim));
+        }
+    };
+    auto stageC = [&](uint32_t x, const Ent& e) {
+        __stcs(opos + x, pos00 + e.rel);  // streaming stores: the outputs are not read again here
+        if (want_sk) __stcs(osk + x, e.sk);
+        const uint32_t sh = (tsh + 2u * e.rel) & 31u;
+        if (VB == 64) {
+            const uint32_t vl = __funnelshift_r(e.w[0], e.w[NW > 1 ? 1 : 0], sh) & mlo;
+            const uint32_t vh = __funnelshift_r(e.w[NW > 1 ? 1 : 0], e.w[NW > 2 ? 2 : 0], sh) & mhi;
+            uint64_t v = ((uint64_t)vh << 32) | vl;
+            if (canon_val) {
+                const uint64_t r = revcomp64(v, len);
+                v = r < v ? r : v;
+            }
+            __stcs(oval + x, (unsigned long long)v);
+        } else if (VB == 128) {
+            uint64_t vlo = (uint64_t)__funnelshift_r(e.w[0], e.w[NW > 1 ? 1 : 0], sh) | ((uint64_t)__funnelshift_r(e.w[NW > 1 ? 1 : 0], e.w[NW > 2 ? 2 : 0], sh) << 32);
+            uint64_t vhi = (uint64_t)__funnelshift_r(e.w[NW > 2 ? 2 : 0], e.w[NW > 3 ? 3 : 0], sh) |
+                           ((uint64_t)__funnelshift_r(e.w[NW > 3 ? 3 : 0], e.w[NW > 4 ? 4 : 0], sh) << 32);
+            if (len <= 32) {
+                vhi = 0;
+                if (len < 32) vlo &= (1ull << (2 * len)) - 1ull;
+            } else if (len < 64) {
+                vhi &= (1ull << (2 * (len - 32))) - 1ull;
+            }
+            uint64_t olo = vlo, ohi = vhi;
+            if (canon_val) {
+                // reverse the 128-bit value 2 bits at a time, complement, shift down by 128 - 2*len
+                const uint64_t rhi = swap_pairs64(__brevll(vlo)) ^ 0xAAAAAAAAAAAAAAAAull;
+                const uint64_t rlo = swap_pairs64(__brevll(vhi)) ^ 0xAAAAAAAAAAAAAAAAull;
+                const uint32_t s = 128 - 2 * len;  // 0..126, even
+                uint64_t qlo, qhi;
+                if (s == 0) qlo = rlo, qhi = rhi;
+                else if (s < 64) qlo = (rlo >> s) | (rhi << (64 - s)), qhi = rhi >> s;
+                else qlo = rhi >> (s - 64), qhi = 0;
+                if (qhi < vhi || (qhi == vhi && qlo < vlo)) olo = qlo, ohi = qhi;
+            }
+            // 16-byte streaming store (consecutive lanes -> 512 contiguous bytes per warp)
+            asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(oval + 2ull * x), "l"(olo), "l"(ohi) : "memory");
+        }
+    };
+    // software pipeline, unrolled twice (two register sets instead of copies): entry x + 32 is
+    // located and its words are requested while entry x is turned into a value and stored
+    Ent e0, e1;
+    uint32_t x = lane;
+    if (x < total) stageB(x, e0);
+#pragma unroll 1
+    while (x < total) {
+        if (x + 32 < total) stageB(x + 32, e1);
+        stageC(x, e0);
+        x += 32;
+        if (x >= total) break;
+        if (x + 32 < total) stageB(x + 32, e0);
+        stageC(x, e1);
+        x += 32;
+    }
+}
+
+// Out-of-line emission for everything that is not the hot single-sequence case: batch mode
+// (positions relative to the read / piece that owns the entry) and tiles whose queues were spilled.
+// Entry i of lane t lives at ebase + i * sI + t * sT (shared-memory queue rows or the spill area).
+template <int VB, bool XW>
+static __device__ __noinline__ void fast_emit_generic(const KArgs& a, uint32_t tile, unsigned long long gbase, uint32_t total,
+                                                    const uint32_t* tp, const unsigned char* ebase, uint32_t sI, uint32_t sT) {
+    using QT = typename std::conditional<XW, uint32_t, uint16_t>::type;
+    constexpr uint32_t DBITS = XW ? 8 : 5, DMASK = (1u << DBITS) - 1u;
+    const uint32_t lane = threadIdx.x & 31u;
+    const uint32_t Wr = a.w;
+    const bool minim = a.mode == MODE_MINIMIZER, want_sk = a.want_sk != 0, canon_val = a.val_canonical != 0;
+    uint32_t* const opos = a.pos + gbase;
+    uint32_t* const osk = a.sk + (want_sk ? gbase : 0ull);
+    unsigned long long* const oval = reinterpret_cast<unsigned long long*>(a.val) + (VB ? gbase * (VB / 64) : 0ull);
+    const int64_t back = 1 + (int64_t)(a.lead - Wr);
+    uint32_t t = 0, lo = 0, hi = tp[1];
+#pragma unroll 1
+    for (uint32_t x = lane; x < total; x += 32) {
+        while (x >= hi) {
+            t++;
+            lo = hi;
+            hi = tp[t + 1];
+        }
+        const uint32_t v = *reinterpret_cast<const QT*>(ebase + (size_t)(x - lo) * sI + (size_t)t * sT);
+        const uint32_t posl = v >> DBITS, wst = posl + (v & DMASK) - (Wr - 1u);
+        uint64_t startbits = 0;
+        int64_t first;  // reported position of local element 0 (relative to the read in batch mode)
+        if (a.n_reads == 0) {
+            first = (int64_t)(a.wbeg + ((uint64_t)tile * 32u + t) * a.S) - back;
+        } else {
+            const uint64_t pi = (uint64_t)tile * 32u + t;
+            const uint64_t r = a.piece_read ? a.piece_read[pi] : pi;
+            const uint32_t win0 = a.piece_read ? a.piece_win0[pi] : 0u;
+            startbits = a.read_start_bp ? 2 * a.read_start_bp[r] : r * a.stride_bits;
+            first = (int64_t)win0 - back;
+        }
+        const uint32_t p = (uint32_t)(first + (minim ? posl : wst));
+        opos[x] = p;
+        if (want_sk) osk[x] = (uint32_t)(first + wst);
+        const uint64_t bit = (uint64_t)((int64_t)startbits + 2 * (int64_t)p + a.bitbias);
+        if (VB == 64) {
+            oval[x] = kmer_value_u64(a, bit, a.val_len, canon_val);
+        } else if (VB == 128) {
+            uint64_t vlo, vhi;
+            kmer_value_u128(a, bit, a.val_len, canon_val, vlo, vhi);
+            reinterpret_cast<ulonglong2*>(oval)[x] = make_ulonglong2(vlo, vhi);
+        }
+    }
 }
 
 // AMB: windows that contain an ambiguous base (a.amb, one bit per base) produce nothing
@@ -156,27 +440,32 @@ __device__ __forceinline__ uint32_t get_byte(uint32_t w, int J) {
 // they go through a small per-warp ring of rows in the L2 scratch, and the minimum of the real
 // window is the minimum over the T+1 shifted sub-windows that cover it (the current one from
 // registers, the others read back from the ring a group of four k-mers ahead of use).  Everything
-// downstream (flags, position bytes, strand fix-up, emission) sees the real-window result.
+// downstream (tie test, queue, emission) sees the real-window result.
 template <int W, bool HC, bool LR, bool SYNC, bool AMB = false, bool XW = false>
-__global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs a) {
+__global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid_constant__ KArgs a) {
     static_assert(W >= 1 && W <= (int)FAST_MAX_W, "W out of range");
     constexpr int B = (int)fast_b(W);    // van-Herk blocks per loop iteration
     constexpr int SB = B * W;            // k-mers per loop iteration (<= 32)
-    constexpr int WQ = (SB + 3) / 4;     // record words per iteration
     constexpr uint32_t NT = FAST_NT;
+    using QT = typename std::conditional<XW, uint32_t, uint16_t>::type;
+    constexpr int ROWB = 32 * (int)sizeof(QT);            // bytes per queue row
+    constexpr uint32_t DBITS = XW ? 8 : 5, DMUL = (1u << DBITS) - 1u;  // entry = pos << DBITS | (window end - pos)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     uint4* T = reinterpret_cast<uint4*>(smem_raw);
     uint32_t* misc = reinterpret_cast<uint32_t*>(T + 256 * FAST_TC);
-    const uint32_t LCAP = a.list_cap;
-    uint32_t* const list = misc + 8 + warp * LCAP;  // this warp's staging list
+    const uint32_t QROWS = a.q_rows;
+    // this warp's lane offsets and queues, two tiles in flight
+    uint32_t* const tp0 = misc + 16 + warp * (2 * FAST_TOFFS);
+    unsigned char* const q0 = reinterpret_cast<unsigned char*>(misc + 16 + FAST_WARPS * 2 * FAST_TOFFS) + (size_t)warp * 2 * QROWS * ROWB;
+    const uint32_t q0s = (uint32_t)__cvta_generic_to_shared(q0) + lane * (uint32_t)sizeof(QT);
     const uint32_t Wr = XW ? a.w : (uint32_t)W;  // real window length
-    const uint32_t NBmax = fast_nb(a.S, Wr);
-    // flag words of this warp, two tiles in flight: fl0[buf][b*32 + lane]
-    uint32_t* const fl0 = misc + 8 + FAST_WARPS * LCAP + (size_t)warp * 2 * NBmax * 32;
-    // this warp's record rows in global scratch (two buffers): row r, lane t -> sc0[buf][r*32 + t]
-    uint32_t* const sc0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * (2 * a.scratch_words_per_block + a.r1_words_per_warp);
-    uint32_t* const r1 = sc0 + 2 * a.scratch_words_per_block;  // XW: level-1 rows of this warp
+    const uint32_t lead = a.lead, NB = a.nb;
+    // spill area (global, per warp and buffer) and the XW ring
+    const size_t spill_words = a.scratch_words_per_block;
+    uint32_t* const sc0 = a.scratch + ((size_t)blockIdx.x * FAST_WARPS + warp) * (2 * spill_words + a.r1_words_per_warp);
+    uint32_t* const r1 = sc0 + 2 * spill_words;  // XW: level-1 rows of this warp
+    const uint32_t SPILLCAP = NB * (uint32_t)SB;  // entries per lane in the spill area
 
     const uint32_t k = a.k, R = a.rot & 31u, R2 = (2u * R) & 31u;
     // ---- table: index byte = in0 | in1<<2 | out0<<4 | out1<<6 (two consecutive bases) --------
@@ -209,50 +498,56 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
         const uint2 e = T2[idx * TCOPIES + tcopy];
         return make_uint4(e.x, e.y, 0u, 0u);
     };
-    uint32_t one;
-    asm volatile("mov.u32 %0, 1;" : "=r"(one));  // opaque constant 1 for imad()
+    // opaque 1 for imad(): a kernel argument, so that ptxas cannot fold x * 1 + c back into an
+    // ALU-pipe add (the positions and the queue pointer are bumped on the idle FMA pipe)
+    const uint32_t one = a.one;
+    const uint32_t rowb = one * (uint32_t)ROWB;
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
     const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (Wr - 1) / 2, so2 = a.mode == MODE_CLOSED ? Wr - 1 : (Wr - 1) / 2;
 
     __syncthreads();  // table + misc ready; from here on every warp works on its own
-    const bool minim = a.mode == MODE_MINIMIZER;
 
     // Software pipeline over tiles: the look-back + emission of tile A runs after the main loop
     // of the next tile B, so A's predecessors have published their counts by then.
-    uint32_t p_valid = 0, p_tile = 0, p_cnt = 0, p_NB = 0, p_inc = 0, cur = 0;
+    uint32_t p_valid = 0, p_tile = 0, p_cnt = 0, p_inc = 0, p_spilled = 0, cur = 0;
     for (;;) {  // persistent: one tile (32 threads x S windows) per iteration, per warp
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(a.ticket, 1u);
         tile = __shfl_sync(0xffffffffu, tile, 0);
         const bool have = tile < a.num_tiles;
-        uint32_t cnt = 0, NB = 0, inc = 0;
+        uint32_t cnt = 0, inc = 0, tile_spilled = 0;
         if (have) {
-        const Segment sg = make_segment_nt(a, tile, lane, 32u);
-        uint32_t* const scr = sc0 + (size_t)cur * a.scratch_words_per_block + lane;
-        uint32_t* const flp = fl0 + (size_t)cur * NBmax * 32 + lane;
-
-        if (sg.nvalid) {
+        const FSeg sg = make_fseg(a, tile, lane);
+        const uint32_t qa0 = q0s + cur * QROWS * (uint32_t)ROWB;   // this lane's first row (shared address)
+        const uint32_t qtrig = qa0 + a.q_trig * (uint32_t)ROWB;
+        QT* const spill = reinterpret_cast<QT*>(sc0 + (size_t)cur * spill_words) + (size_t)lane * SPILLCAP;
+        uint32_t qa = qa0, spilled = 0;
+        {
             uint32_t fw = misc[1], rc = misc[2];
-            const uint32_t nelem = sg.nvalid + sg.has_prev + (Wr - 1);
-            NB = (nelem + SB - 1) / SB;
-            // first/last valid window-end element: e = jl + W - 1, jl in [has_prev, has_prev + nvalid)
-            const uint32_t e_lo = sg.has_prev + (Wr - 1), e_hi = e_lo + sg.nvalid;
+            // last valid window-end element + 1 (the first one is `lead` for every thread)
+            const uint32_t e_hi = lead + sg.nvalid;
 
-            // ---- thread-local view of the packed stream (32-bit word offsets) ----------------
+            // ---- thread-local view of the packed stream (32-bit word offsets from w0abs) -----
             // Entering bases of block b start at local base k-1+bW; leaving bases at local base
             // bW-1 (base -1 = virtual 'A').  Both are addressed with one extra virtual word in
             // front (+32 bits) so that the bit position never goes negative.
-            const uint64_t w0abs = sg.bit0 >> 5;
-            const uint32_t* const wbase = a.seq + w0abs;
+            const int64_t w0abs = sg.bit0 >> 5;
+            const uint32_t* const wbase = a.seq + w0abs;   // only dereferenced inside the buffer
             const uint32_t sh0 = (uint32_t)sg.bit0 & 31u;
-            const uint64_t remw = a.seq_nwords - 1 - w0abs;
-            const uint32_t wlim = remw > 0x7ffffff0ull ? 0x7ffffff0u : (uint32_t)remw;
+            // may any (pre)fetch of this thread touch a word outside the buffer?
+            const uint32_t wmax = ((sh0 + 32u + 2u * (k - 1) + 2u * (NB + 1) * SB) >> 5) + 3u;
+            const bool clampd = w0abs < 1 || (uint64_t)w0abs + wmax >= a.seq_nwords;
+            auto ldw = [&](uint32_t wl1) -> uint32_t {  // wl1 = word offset + 1 (virtual word 0)
+                if (wl1 == 0) return 0u;
+                if (clampd) return ld_word_any(a.seq, a.seq_nwords, w0abs + (int64_t)wl1 - 1);
+                return __ldg(wbase + (wl1 - 1));
+            };
             // ---- prologue: consume k-1 bases, two per table step (leaving bases = virtual 'A') --
             {
-                uint32_t pp = sh0, rem = k - 1;
+                uint32_t pp = sh0 + 32u, rem = k - 1;
                 while (rem) {
-                    const uint32_t wl = pp >> 5, sh = pp & 31u;
-                    uint32_t x = __funnelshift_r(__ldg(wbase + min(wl, wlim)), __ldg(wbase + min(wl + 1, wlim)), sh);
+                    const uint32_t wl1 = pp >> 5, sh = pp & 31u;
+                    uint32_t x = __funnelshift_r(ldw(wl1), ldw(wl1 + 1), sh);
                     uint32_t take = min(rem, 16u);
                     rem -= take;
                     pp += 32u;
@@ -270,14 +565,6 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
             }
             uint32_t pin = sh0 + 32u + 2u * (k - 1);  // bit position (+32) of the entering stream
             uint32_t pout = sh0 + 30u;                // bit position (+32) of the leaving stream
-            // may any (pre)fetch of this thread touch a word past the end of the buffer?
-            const bool clampd = ((pin + 2u * (NB + 1) * SB) >> 5) + 2u > wlim;
-            auto ldw = [&](uint32_t wl1) -> uint32_t {  // wl1 = word offset + 1 (virtual word 0)
-                if (wl1 == 0) return 0u;
-                uint32_t wl = wl1 - 1;
-                if (clampd) wl = min(wl, wlim);
-                return __ldg(wbase + wl);
-            };
             uint32_t iw0 = ldw(pin >> 5), iw1 = ldw((pin >> 5) + 1), iw2 = SB > 16 ? ldw((pin >> 5) + 2) : 0u;
             uint32_t ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1), ow2 = SB > 16 ? ldw((pout >> 5) + 2) : 0u;
             ow0 &= ~(3u << (pout & 31u));  // element 0 leaves the virtual 'A'
@@ -285,23 +572,39 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
             uint32_t RL[W], RR[W];
 #pragma unroll
             for (int t = 0; t < W; t++) RL[t] = 0xffffffffu, RR[t] = 0u;
-            uint32_t prev = 0xffffffffu, prevlow = 0x100u;
-            uint32_t* sp = scr;
+            uint32_t prev = 0xffffffffu;
             // XW: window of Wr k-mers ending at e = min over the sub-windows (W k-mers) ending at
             // e, e - W, ..., e - (T-1) W and e - (Wr - W); consecutive ones overlap or abut
             const uint32_t Dmax = Wr - W, T = XW ? (Wr + W - 1) / W - 1 : 0u;
             const uint32_t rmask = XW ? fast_ring_rows(Wr) - 1u : 0u;
             uint32_t tL[4] = {0, 0, 0, 0}, tR[4] = {0, 0, 0, 0};
-            // ambiguity: only threads whose stretch holds an ambiguous base do any work per block
+            // ambiguity: only threads whose stretch holds an ambiguous base compute clean masks
             bool amb_here = false;
-            uint32_t zrun = 0, pclean = 0;
-            uint64_t ab0 = 0;
+            uint32_t zrun = 0, pclean = 1;
+            int64_t ab0 = 0;
             if (AMB) {
-                ab0 = (uint64_t)((int64_t)sg.pos_base + a.amb_bitbias);
-                amb_here = amb_any(a, ab0, nelem + k - 1);
+                // mask bit of local base 0 (bases in front of the sequence count as unambiguous)
+                ab0 = ((sg.bit0 - a.bitbias) >> 1) + a.amb_bitbias;
+                amb_here = amb_any(a, ab0, NB * SB + k - 1);
                 if (amb_here) zrun = amb_clean_run(a, ab0, k - 1);
             }
+            // the iteration after which the lead-in ends (B == 1); B > 1: after block 0 of iteration 0
+            const uint32_t lead_b = lead / (uint32_t)SB - (B == 1 ? 1u : 0u);
 
+            // a lane close to the end of its rows: the warp moves all its queues to the spill area
+            auto spill_check = [&](uint32_t b) {
+                if (__builtin_expect(__any_sync(0xffffffffu, qa > qtrig), 0)) {
+                    if (B == 1 && b <= lead_b) {
+                        qa = qa0;  // still inside the lead-in: nothing pushed so far is kept anyway
+                    } else {
+                        const uint32_t n = (qa - qa0) / (uint32_t)ROWB;
+                        q_spill<ROWB, XW, QT>(qa0, n, spill + spilled);
+                        spilled += n;
+                        qa = qa0;
+                        tile_spilled = 1;
+                    }
+                }
+            };
             for (uint32_t b = 0; b < NB; b++) {
                 const uint32_t eb = b * SB;
                 const uint32_t shi = pin & 31u, sho = pout & 31u;
@@ -321,10 +624,17 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                     ow0 = ldw(pout >> 5), ow1 = ldw((pout >> 5) + 1);
                     if (SB > 16) iw2 = ldw((pin >> 5) + 2), ow2 = ldw((pout >> 5) + 2);
                 }
-                uint32_t preL = 0, preR = 0, bf = 0, lastR = 0;
-                uint32_t accL[WQ], accR[WQ];
-#pragma unroll
-                for (int q = 0; q < WQ; q++) accL[q] = 0, accR[q] = 0;
+                uint32_t preL = 0, preR = 0;
+                uint32_t gr[4] = {0, 0, 0, 0}, gm[4] = {0, 0, 0, 0}, gp[4] = {0, 0, 0, 0};  // group of four windows
+                uint32_t clean = 0xffffffffu;
+                if (AMB && amb_here) {
+                    // window ending at k-mer eb+t = the l bases ending at local base eb+t+k-1.
+                    // A clean window right after an ambiguous one is always emitted: the
+                    // reference compares against SKIPPED there (src/intrinsics/dedup.rs:147-155).
+                    const uint2 cm = amb_clean_mask(a, ab0 + eb + (k - 1), SB, a.l, zrun);
+                    clean = cm.x;
+                    zrun = cm.y;
+                }
 #pragma unroll
                 for (int j = 0; j < B; j++) {  // van-Herk block j of this iteration
                 const int o = j * W;           // its first k-mer inside the iteration
@@ -444,31 +754,54 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                         res0 = min(res0, tL[t & 3]);
                         if (two) res1 = min(res1, tL[(t + 1) & 3]);
                     }
-                    if (LR) {
-                        accR[(o + t) >> 2] = put_byte(accR[(o + t) >> 2], mR0, (o + t) & 3);
-                        if (two) {
-                            accR[(o + t + 1) >> 2] = put_byte(accR[(o + t + 1) >> 2], mR1, (o + t + 1) & 3);
+                    // ---- group of four windows: tie test, then one queue entry per new selection ----
+                    gr[t & 2] = res0, gm[t & 2] = mR0, gp[t & 2] = pos0;
+                    if (two) gr[(t & 2) + 1] = res1, gm[(t & 2) + 1] = mR1, gp[(t & 2) + 1] = pos1;
+                    if ((t & 2) || t + 2 >= W) {
+                        const int g0 = t & ~3;                    // first window of the group (inside the block)
+                        const int ng = W - g0 < 4 ? W - g0 : 4;   // windows in it
+                        if (LR) {
+                            // leftmost != rightmost in one of them?  res ^ mR has all sixteen key bits
+                            // set and the xor of the two positions below them.  Cold: strand rule.
+                            uint32_t tie = gr[0] ^ gm[0];
+#pragma unroll
+                            for (int u = 1; u < 4; u++)
+                                if (u < ng) tie |= gr[u] ^ gm[u];
+                            if (__builtin_expect(tie != 0xffff0000u, 0)) {
+                                const uint4 f = tie_fix4(a, sg.bit0, gp[0], (uint32_t)ng, make_uint4(gr[0], gr[1], gr[2], gr[3]),
+                                                         make_uint4(gm[0], gm[1], gm[2], gm[3]));
+                                gr[0] = f.x, gr[1] = f.y, gr[2] = f.z, gr[3] = f.w;
+                            }
                         }
-                        if (o + t == SB - 1) lastR = mR0;
-                        if (o + t + 1 == SB - 1) lastR = mR1;
+#pragma unroll
+                        for (int u = 0; u < 4; u++) {
+                            if (u >= ng) continue;
+                            const int tt = o + g0 + u;            // window inside the iteration
+                            const uint32_t r = gr[u], ps = gp[u];
+                            const uint32_t ent = XW ? imad(r & 0xffffu, DMUL, ps) : imad(r, DMUL, ps);
+                            if (!SYNC && !AMB) {
+                                q_push_ne_fma<XW>(qa, r, prev, ent, rowb, one);
+                                prev = r;
+                            } else {
+                                bool pe;
+                                if (SYNC) {
+                                    const uint32_t d = ps - (r & 0xffffu);
+                                    pe = d == so1 || d == so2;
+                                } else {
+                                    pe = r != prev;
+                                    prev = r;
+                                }
+                                if (AMB) {
+                                    const bool c = (clean >> tt) & 1u;
+                                    const bool cm1 = tt ? ((clean >> ((tt ? tt : 1) - 1)) & 1u) : (pclean != 0u);
+                                    if (!SYNC) pe = pe || !cm1;
+                                    pe = pe && c;
+                                }
+                                q_push_if<ROWB, XW>(qa, pe, ent);
+                            }
+                        }
+                        if (XW) spill_check(b);
                     }
-                    if (SYNC) {
-                        const uint32_t d0 = pos0 - (res0 & 0xffffu);
-                        if (d0 == so1 || d0 == so2) bf |= 1u << (o + t);
-                        if (two) {
-                            const uint32_t d1 = pos1 - (res1 & 0xffffu);
-                            if (d1 == so1 || d1 == so2) bf |= 1u << (o + t + 1);
-                        }
-                    } else {
-                        or_if_ne(bf, res0, prev, 1u << (o + t));
-                        prev = res0;
-                        if (two) {
-                            or_if_ne(bf, res1, prev, 1u << (o + t + 1));
-                            prev = res1;
-                        }
-                    }
-                    accL[(o + t) >> 2] = put_byte(accL[(o + t) >> 2], res0, (o + t) & 3);
-                    if (two) accL[(o + t + 1) >> 2] = put_byte(accL[(o + t + 1) >> 2], res1, (o + t + 1) & 3);
                 }
                 // suffix minima of this block (slot 0 is never needed)
 #pragma unroll
@@ -476,68 +809,34 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
                     RL[q] = min(RL[q], RL[q + 1]);
                     if (LR) RR[q] = max(RR[q], RR[q + 1]);
                 }
-                }  // van-Herk blocks of this iteration
-                // leftmost != rightmost somewhere in this iteration?  Compare the position bytes,
-                // four windows per LOP3 (positions inside a window differ by < 256)
-                uint32_t tacc = 0;
-                if (LR) {
-#pragma unroll
-                    for (int q = 0; q < WQ; q++) tacc |= accL[q] ^ accR[q];
-                }
-                if (LR && tacc != 0u) {
-                    // cold: some window of this block has leftmost != rightmost.  Apply the strand
-                    // rule to those windows and rebuild the block's flags from the position bytes.
-                    bf = 0;
-                    uint32_t pl = prevlow;
-#pragma unroll
-                    for (int t = 0; t < SB; t++) {
-                        uint32_t cur = get_byte(accL[t >> 2], t & 3);
-                        const uint32_t rgt = get_byte(accR[t >> 2], t & 3);
-                        if (cur != rgt && eb + t >= Wr - 1u) {
-                            if (!window_prefers_left(wbase, sh0, wlim, 2u * (eb + t - (Wr - 1u)), a.l)) {
-                                cur = rgt;
-                                accL[t >> 2] = put_byte(accL[t >> 2], rgt, t & 3);
-                                if (t == SB - 1) prev = lastR ^ 0xffff0000u;
-                            }
-                        }
-                        if (SYNC) {
-                            const uint32_t d = (eb + t - cur) & 0xffu;
-                            if (d == so1 || d == so2) bf |= 1u << t;
-                        } else {
-                            if (cur != pl) bf |= 1u << t;
-                            pl = cur;
-                        }
+                // end of the lead-in: everything pushed so far belongs to windows in front of the
+                // segment; the last of them seeds the dedup comparison unless nothing is in front
+                if ((B > 1 && j == 0) || (B == 1 && j == B - 1)) {
+                    if (b == lead_b) {
+                        qa = qa0;
+                        spilled = 0;
+                        if (sg.first_always) prev = 0xffffffffu;
                     }
                 }
-                prevlow = get_byte(accL[(SB - 1) >> 2], (SB - 1) & 3);
-                uint32_t clean = 0xffffffffu;
-                if (AMB && amb_here) {
-                    // window ending at k-mer eb+t = the l bases ending at local base eb+t+k-1.
-                    // A clean window right after an ambiguous one is always emitted: the
-                    // reference compares against SKIPPED there (src/intrinsics/dedup.rs:147-155).
-                    const uint2 cm = amb_clean_mask(a, ab0 + eb + (k - 1), SB, a.l, zrun);
-                    clean = cm.x;
-                    zrun = cm.y;
-                    if (!SYNC) bf |= ~((clean << 1) | pclean);
-                    pclean = (clean >> (SB - 1)) & 1u;
-                }
-                // keep flags of valid windows only: bit t <-> window-end element eb + t
-                // (only the first and last blocks of a segment can hold invalid windows)
-                if (eb < e_lo + 1u || eb + SB > e_hi) {
-                    const uint32_t lo = e_lo > eb ? min(e_lo - eb, (uint32_t)SB) : 0u;
-                    const uint32_t hi = e_hi > eb ? min(e_hi - eb, (uint32_t)SB) : 0u;
-                    const uint32_t mhi = hi >= 32u ? 0xffffffffu : ((1u << hi) - 1u);
-                    const uint32_t mlo = lo >= 32u ? 0xffffffffu : ((1u << lo) - 1u);
-                    if (!SYNC && sg.first_always && e_lo >= eb && e_lo < eb + SB) bf |= 1u << (e_lo - eb);
-                    bf &= mhi & ~mlo;
-                }
-                if (AMB) bf &= clean;
-                flp[b * 32] = bf;
-#pragma unroll
-                for (int q = 0; q < WQ; q++) sp[q * 32] = accL[q];
-                sp += WQ * 32;
-                cnt += __popc(bf);
+                }  // van-Herk blocks of this iteration
+                if (AMB) pclean = (clean >> (SB - 1)) & 1u;
+                if (!XW) spill_check(b);
             }
+            // ---- count: rows pushed, minus those of windows behind the segment's last one ------
+            uint32_t n = (qa - qa0) / (uint32_t)ROWB;
+            if (tile_spilled) {  // warp-uniform: everything goes to the spill area
+                q_spill<ROWB, XW, QT>(qa0, n, spill + spilled);
+                n += spilled;
+            }
+            if (__any_sync(0xffffffffu, e_hi != NB * (uint32_t)SB)) {
+                if (sg.nvalid == 0) n = 0;
+                while (n) {
+                    const uint32_t v = tile_spilled ? (uint32_t)spill[n - 1] : q_load<XW>(qa0 + (n - 1) * (uint32_t)ROWB);
+                    if ((v >> DBITS) + (v & DMUL) < e_hi) break;
+                    n--;
+                }
+            }
+            cnt = n;
         }
         // publish this tile's count (aggregate) right away; its prefix is resolved one tile later
         __syncwarp();
@@ -548,16 +847,15 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
             if (lane >= (uint32_t)o) inc += v;
         }
         if (lane == 31) st_state(a.tile_state + tile, ((unsigned long long)inc << 2) | 1ull);
+        uint32_t* const tp = tp0 + cur * FAST_TOFFS;
+        tp[lane] = inc - cnt;
+        if (lane == 31) tp[32] = inc;
         }  // have
 
         // ---- ordered emission of the PREVIOUS tile, warp-autonomous (no block barriers) --------
         if (p_valid) {
-        const uint32_t tile_e = p_tile, cnt_e = p_cnt, NB_e = p_NB, inc_e = p_inc;
-        (void)NB_e;
-        const uint32_t* const scr0 = pinned(sc0 + (size_t)(cur ^ 1u) * a.scratch_words_per_block);
-        const uint32_t* const flr = fl0 + (size_t)(cur ^ 1u) * NBmax * 32 + lane;
+        const uint32_t tile_e = p_tile, inc_e = p_inc, pb = cur ^ 1u;
         const uint32_t total = __shfl_sync(0xffffffffu, inc_e, 31);
-        const uint32_t toff = inc_e - cnt_e;
         const unsigned long long gbase = lookback_excl(a.tile_state, tile_e, total);
         if (lane == 0 && tile_e == a.num_tiles - 1) {
             *a.count_out = gbase + total;
@@ -570,160 +868,62 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const KArgs 
         }
         if (a.n_reads != 0) write_csr_offset(a, (uint64_t)tile_e * 32u + lane, gbase + inc_e);
         if (!ovf && total != 0) {
-
-        // Tile-uniform addressing (32-bit offsets from the tile's first thread).
-        const bool canon_val = a.val_canonical != 0;
-        const uint64_t j00 = a.wbeg + (uint64_t)tile_e * 32u * a.S;  // first window of the tile
-        const uint32_t hp0 = (a.n_reads == 0 && j00 > 0 && minim) ? 1u : 0u;
-        const uint64_t tbit0 = (uint64_t)((int64_t)(2 * (j00 - hp0)) + a.bitbias);  // lane 0's bit0
-        const uint32_t* const twbase = pinned(a.seq + (tbit0 >> 5));
-        const uint32_t tsh = (uint32_t)tbit0 & 31u;
-        const uint64_t trem = a.seq_nwords - 1 - (tbit0 >> 5);
-        const uint32_t twlim = trem > 0x7ffffff0ull ? 0x7ffffff0u : (uint32_t)trem;
-        const bool tclamp = ((tsh + 2u * (32u * a.S + a.l + 64u)) >> 5) + 3u > twlim;
-        const uint32_t pos00 = (uint32_t)j00;
-
-        // Every lane walks its own flag words (coalesced across lanes) and stages its entries at
-        // [toff, toff + cnt) of the tile's output range; list_cap entries per pass.
-        uint32_t bq = 0, produced = 0;
-        uint32_t f = (cnt_e != 0) ? flr[0] : 0u;
-        for (uint32_t cbase = 0; cbase < total; cbase += LCAP) {
-            while (produced < cnt_e && toff + produced < cbase + LCAP) {
-                while (f == 0) {
-                    bq++;
-                    f = flr[bq * 32];
-                }
-                const uint32_t bit = (uint32_t)__ffs(f) - 1u;
-                f &= f - 1u;
-                list[toff + produced - cbase] = (lane << 16) | (bq << 5) | bit;  // owner | iteration | bit
-                produced++;
-            }
             __syncwarp();
-            const uint32_t nent = min(LCAP, total - cbase);
-            uint32_t* const opos = pinned(a.pos + (gbase + cbase));
-            uint32_t* const osk = pinned(a.sk + (a.want_sk ? gbase + cbase : 0ull));
-            unsigned long long* const oval = pinned(reinterpret_cast<unsigned long long*>(a.val) + (a.value_bits == 64 ? gbase + cbase : 0ull));
-            if (a.n_reads == 0 && a.value_bits != 0) {
-            // Single sequence with values: one software-pipelined pass over the staged entries (entry x is
-            // handled by lane x & 31 in all stages, so nothing goes back through shared memory).
-            //   stage A (entry x+64): descriptor -> load of the position byte from the L2 scratch
-            //   stage B (entry x+32): position -> loads of the k-mer's words from the sequence
-            //   stage C (entry x):    value, coalesced streaming stores of pos / sk / val
-            // Both dependent load latencies are overlapped with the work of the previous entries.
-            const bool want64 = a.value_bits == 64;
-            uint32_t dA = 0, wvA = 0;                              // stage A -> B
-            uint32_t relB = 0, skB = 0, w0 = 0, w1 = 0, w2 = 0;    // stage B -> C
-            auto stageA = [&](uint32_t x) {
-                dA = list[x];
-                const uint32_t t2 = dA >> 16, b2 = (dA >> 5) & 0x7ffu, bit2 = dA & 31u;
-                wvA = __ldcg(scr0 + (size_t)(b2 * WQ + (bit2 >> 2)) * 32 + t2);
-            };
-            auto stageB = [&]() {
-                const uint32_t t2 = dA >> 16, b2 = (dA >> 5) & 0x7ffu, bit2 = dA & 31u, e = b2 * SB + bit2;
-                const uint32_t lowb = (wvA >> (8u * (bit2 & 3u))) & 0xffu;
-                const uint32_t jl = e - (Wr - 1);  // local window index of the owner
-                const uint32_t local = minim ? jl + ((lowb - jl) & 0xffu) : jl;
-                // owner's local base 0 = tile base + t2*S (- has_prev, which only differs for
-                // the very first thread of the sequence)
-                const uint32_t hp = (minim && !(j00 == 0 && t2 == 0)) ? 1u : 0u;
-                relB = t2 * a.S - hp + hp0 + local;  // bases from the tile's bit0
-                skB = pos00 + t2 * a.S + (jl - hp);
-                if (want64) {
-                    const uint32_t wl = (tsh + 2u * relB) >> 5;
-                    if (!tclamp) {
-                        const uint32_t* pw = twbase + wl;
-                        w0 = __ldg(pw), w1 = __ldg(pw + 1), w2 = __ldg(pw + 2);
-                    } else {
-                        w0 = __ldg(twbase + min(wl, twlim)), w1 = __ldg(twbase + min(wl + 1, twlim));
-                        w2 = __ldg(twbase + min(wl + 2, twlim));
-                    }
-                }
-            };
-            uint32_t x = lane;
-            if (x < nent) {
-                stageA(x);
-                stageB();
-            }
-            if (x + 32 < nent) stageA(x + 32);
-#pragma unroll 1
-            for (; x < nent; x += 32) {
-                const uint32_t rel = relB, skv = skB, c0 = w0, c1 = w1, c2 = w2;
-                if (x + 32 < nent) stageB();
-                if (x + 64 < nent) stageA(x + 64);
-                __stcs(opos + x, pos00 - hp0 + rel);  // streaming store: keep the L2 for the scratch rows
-                if (a.want_sk) __stcs(osk + x, skv);
-                if (want64) {
-                    const uint32_t sh = (tsh + 2u * rel) & 31u;
-                    const uint32_t vlo = __funnelshift_r(c0, c1, sh), vhi = __funnelshift_r(c1, c2, sh);
-                    uint64_t v = (uint64_t)vlo | ((uint64_t)vhi << 32);
-                    const uint32_t len = a.val_len;
-                    if (len < 32) v &= (1ull << (2 * len)) - 1ull;
-                    if (canon_val) {
-                        const uint64_t r = (swap_pairs64(__brevll(v)) ^ 0xAAAAAAAAAAAAAAAAull) >> (64 - 2 * len);
-                        v = r < v ? r : v;
-                    }
-                    __stcs(oval + x, (unsigned long long)v);
-                } else if (a.value_bits == 128) {
-                    uint64_t lo, hi;
-                    kmer_value_u128(a, tbit0 + 2ull * rel, a.val_len, canon_val, lo, hi);
-                    reinterpret_cast<ulonglong2*>(a.val)[gbase + cbase + x] = make_ulonglong2(lo, hi);
-                }
-            }
+            const uint32_t* const tpe = tp0 + pb * FAST_TOFFS;
+            const unsigned char* ebase;
+            uint32_t sI, sT;
+            if (p_spilled) {
+                ebase = reinterpret_cast<const unsigned char*>(sc0 + (size_t)pb * spill_words);
+                sI = (uint32_t)sizeof(QT), sT = SPILLCAP * (uint32_t)sizeof(QT);
+                __threadfence_block();
             } else {
-            // positions only (nothing to overlap: measured 2-3 % faster this way), batch mode: two sweeps
-            // sweep 1: fetch each entry's position byte from the L2 scratch (independent loads,
-            // unrolled so several are in flight) and fold it into the staged descriptor
-#pragma unroll 2
-            for (uint32_t x = lane; x < nent; x += 32) {
-                const uint32_t dsc = list[x];
-                const uint32_t t2 = dsc >> 16, b2 = (dsc >> 5) & 0x7ffu, bit2 = dsc & 31u, e = b2 * SB + bit2;
-                const uint32_t wv = __ldcg(scr0 + (size_t)(b2 * WQ + (bit2 >> 2)) * 32 + t2);
-                const uint32_t lowb = (wv >> (8u * (bit2 & 3u))) & 0xffu;
-                const uint32_t jl = e - (Wr - 1);  // local window index of the owner
-                list[x] = (t2 << 27) | (((lowb - jl) & 0xffu) << 16) | jl;
+                ebase = q0 + (size_t)pb * QROWS * ROWB;
+                sI = (uint32_t)ROWB, sT = (uint32_t)sizeof(QT);
             }
-            __syncwarp();
-            // sweep 2: positions, super-k-mer starts and k-mer values
-#pragma unroll 1
-            for (uint32_t x = lane; x < nent; x += 32) {
-                const uint32_t dsc = list[x];
-                const uint32_t t2 = dsc >> 27, jl = dsc & 0xffffu;
-                const uint32_t local = minim ? jl + ((dsc >> 16) & 0xffu) : jl;
-                if (a.n_reads == 0) {
-                    const uint32_t hp = (minim && !(j00 == 0 && t2 == 0)) ? 1u : 0u;
-                    __stcs(opos + x, pos00 + t2 * a.S - hp + local);
-                    if (a.want_sk) __stcs(osk + x, pos00 + t2 * a.S + (jl - hp));
-                    continue;
-                }
-                const Segment og = make_segment_nt(a, tile_e, t2, 32u);
-                const unsigned long long oi = gbase + cbase + x;
-                a.pos[oi] = (uint32_t)og.pos_base + local;
-                if (a.want_sk) a.sk[oi] = (uint32_t)og.win_base + (jl - og.has_prev);
-                if (a.value_bits == 64) {
-                    a.val[oi] = kmer_value_u64(a, og.bit0 + 2ull * local, a.val_len, canon_val);
-                } else if (a.value_bits == 128) {
-                    uint64_t lo, hi;
-                    kmer_value_u128(a, og.bit0 + 2ull * local, a.val_len, canon_val, lo, hi);
-                    reinterpret_cast<ulonglong2*>(a.val)[oi] = make_ulonglong2(lo, hi);
-                }
-            }
+            if (a.n_reads == 0 && !p_spilled) {
+                const uint32_t qs = q0s - lane * (uint32_t)sizeof(QT) + pb * QROWS * (uint32_t)ROWB;
+                if (a.value_bits == 64) fast_emit_seq<64, XW>(a, tile_e, gbase, total, tpe, qs);
+                else if (a.value_bits == 128) fast_emit_seq<128, XW>(a, tile_e, gbase, total, tpe, qs);
+                else fast_emit_seq<0, XW>(a, tile_e, gbase, total, tpe, qs);
+            } else {
+                if (a.value_bits == 64) fast_emit_generic<64, XW>(a, tile_e, gbase, total, tpe, ebase, sI, sT);
+                else if (a.value_bits == 128) fast_emit_generic<128, XW>(a, tile_e, gbase, total, tpe, ebase, sI, sT);
+                else fast_emit_generic<0, XW>(a, tile_e, gbase, total, tpe, ebase, sI, sT);
             }
             __syncwarp();
         }
-        }  // !ovf && total
         }  // p_valid
         if (!have) break;
-        p_valid = 1, p_tile = tile, p_cnt = cnt, p_NB = NB, p_inc = inc;
+        p_valid = 1, p_tile = tile, p_cnt = cnt, p_inc = inc, p_spilled = tile_spilled;
+        (void)p_cnt;
         cur ^= 1u;
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------
 struct FastPlan {
-    uint32_t S = 0, num_tiles = 0, grid = 0, list_cap = 0;
-    size_t scratch_words_per_block = 0;  // position-byte rows, per warp and buffer
+    uint32_t S = 0, num_tiles = 0, grid = 0, q_rows = 0, q_trig = 0, nb = 0, lead = 0;
+    size_t scratch_words_per_block = 0;  // spill area, per warp and buffer
     size_t r1_words = 0;                 // XW: level-1 rows, per warp
 };
+
+// queue geometry for segments of S windows; false when it does not fit the shared memory
+inline bool fast_queue_plan(uint32_t S, const mz_params& p, FastPlan* pl) {
+    const uint32_t sb = fast_sb(fast_wt(p.w));
+    pl->S = S;
+    pl->lead = fast_lead(p.w);
+    pl->nb = fast_nb(S, p.w);
+    pl->q_trig = fast_q_trig(S, p);
+    // rows pushed between two overflow checks: an iteration (one check at its end), long windows
+    // (4-byte entries, sparse output) check after every group of four windows instead
+    pl->q_rows = pl->q_trig + (p.w > FAST_MAX_W ? 4u : sb);
+    pl->scratch_words_per_block = fast_spill_words(S, p.w);
+    pl->r1_words = fast_r1_words(p.w, p.strand_tiebreak != 0);
+    // entry field widths: selected k-mer below 2^11 (u16 entries) / 2^16 (positions in the keys)
+    const uint32_t elems = pl->nb * sb + 1;
+    if (p.w <= FAST_MAX_W ? elems >= 2048 : elems >= 65535) return false;
+    return fast_smem(p.w, pl->q_rows) <= FAST_SMEM_LIMIT;
+}
 
 // Geometry for the fast kernel; returns false when (k, w, ...) is outside its domain.
 inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan* pl, bool allow_xw = false) {
@@ -733,54 +933,61 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
     const char* env_bps = getenv("MZ_FAST_BPS");
     const uint32_t bps = env_bps ? (uint32_t)atoi(env_bps) : FAST_BPS;  // resident blocks per SM
     const uint64_t slots = (uint64_t)sm_count * bps * FAST_WARPS;  // resident warps
+    const uint32_t sb = fast_sb(fast_wt(p.w)), lead = fast_lead(p.w);
     uint32_t s;
     if (env_s) {
         s = (uint32_t)atoi(env_s);
     } else {
         // long segments amortise the (k+w-2)-base warm-up.  Few waves (small inputs, shards of a
         // multi-GPU run): equal tiles in a whole number of waves, m = 1 .. 8 tiles per warp.
-        const uint32_t smax = xw ? 310u + p.w : 310u;
+        static const uint32_t smax0 = getenv("MZ_FAST_SMAX") ? (uint32_t)atoi(getenv("MZ_FAST_SMAX")) : 420u;
+        const uint32_t smax = xw ? smax0 + p.w : smax0;
         const uint64_t per_wave = slots * 32;
         const uint64_t m = (nwin + per_wave * smax - 1) / (per_wave * smax);
         const uint64_t want = m <= 8 ? (nwin + per_wave * m - 1) / (per_wave * m) : smax;
         s = (uint32_t)std::min<uint64_t>(std::max<uint64_t>(want, 64), smax);
-        // a thread computes S + w k-mers in whole loop iterations of SB k-mers: pick S so that
-        // the last iteration is full (S = NB*SB - w; 288 -> 304 for w = 19 was worth 3 %)
-        const uint32_t sb = fast_sb(fast_wt(p.w));
-        uint32_t nb = std::max<uint32_t>(1, (s + p.w + (m <= 8 ? sb - 1 : 0)) / sb);  // few waves: round up
-        while (nb * sb < p.w + 16) nb++;
-        s = nb * sb - p.w;
-        // dense outputs: shorten the segments until a tile's expected entries fit one staging
-        // pass (a second pass costs more than the longer halo), but keep S >= 160
-        const double dens = p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
-                          : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
-        while (nb > 1 && (nb - 1) * sb >= p.w + 160 && 32.0 * s * dens * 1.15 > fast_list_cap(s, p)) {
-            nb--;
-            s = nb * sb - p.w;
+        // a thread computes lead + S k-mers in whole loop iterations of SB k-mers: pick S so that
+        // the last iteration is full (S = NB*SB - lead)
+        uint32_t nb = std::max<uint32_t>(1, (s + lead + (m <= 8 ? sb - 1 : 0)) / sb);  // few waves: round up
+        while (nb * sb < lead + 16) nb++;
+        s = nb * sb - lead;
+    }
+    s = std::max<uint32_t>(1, s);
+    // the queues live in shared memory: shorten the segments until they fit (dense outputs)
+    while (!fast_queue_plan(s, p, pl)) {
+        if (s <= sb) {
+            if (s <= 1) return false;
+            s = std::max<uint32_t>(1, s / 2);
+        } else {
+            s -= sb;
         }
     }
-    s = std::max<uint32_t>(16, s);
-    // flag words and staging lists live in shared memory: stay within FAST_SMEM_LIMIT
-    while (s > 16 + fast_sb(fast_wt(p.w)) && fast_smem(s, p.w, fast_list_cap(s, p)) > FAST_SMEM_LIMIT) s -= fast_sb(fast_wt(p.w));
-    if ((uint64_t)s + p.w + 2 >= 65535 || fast_nb(s, p.w) >= 2048) return false;  // descriptor: 11-bit iteration
     const uint64_t Tt = (uint64_t)32 * s;
     const uint64_t tiles = (nwin + Tt - 1) / Tt;
     if (tiles == 0 || tiles > 0x7fffffffull) return false;
-    pl->S = s;
-    pl->list_cap = fast_list_cap(s, p);
     pl->num_tiles = (uint32_t)tiles;
     // one block per SM as soon as there are that many tiles (warps take tiles from the ticket
     // counter, so a small launch spreads over all SMs instead of filling a few of them)
     pl->grid = (uint32_t)std::min<uint64_t>(tiles, (uint64_t)sm_count * bps);
-    pl->scratch_words_per_block = fast_scratch_words(s, p.w);
-    pl->r1_words = fast_r1_words(s, p.w, p.strand_tiebreak != 0);
     return true;
+}
+
+// copy a plan's queue geometry into the kernel arguments
+inline void fast_plan_args(const FastPlan& fp, KArgs& a) {
+    a.S = fp.S;
+    a.q_rows = fp.q_rows;
+    a.q_trig = fp.q_trig;
+    a.nb = fp.nb;
+    a.lead = fp.lead;
+    a.one = 1;
+    a.scratch_words_per_block = fp.scratch_words_per_block;
+    a.r1_words_per_warp = fp.r1_words;
 }
 
 template <int W, bool HC, bool LR, bool SYNC, bool AMB = false, bool XW = false>
 inline int launch_fast_inst(uint32_t grid, const KArgs& a, cudaStream_t st) {
     auto kern = mz_fast_kernel<W, HC, LR, SYNC, AMB, XW>;
-    const size_t smem = fast_smem(a.S, XW ? a.w : (uint32_t)W, a.list_cap);
+    const size_t smem = fast_smem(a.w, a.q_rows);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return MZ_ERR_CUDA;

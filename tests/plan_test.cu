@@ -1,6 +1,6 @@
 // Host-only invariants of the fast kernel's launch geometry (no device needed): for every window
-// length and builder the plan must respect the shared-memory limit, the 11-bit iteration field of
-// the staging descriptors, whole-iteration segments, and the sub-window rules of long windows.
+// length and builder the plan must respect the shared-memory limit, the field widths of the
+// queue entries, whole-iteration segments, and the sub-window rules of long windows.
 #include <cstdio>
 #include <cstdlib>
 
@@ -43,14 +43,22 @@ int main() {
                     } else {
                         CHECK(pl.r1_words == 0);
                     }
-                    CHECK(pl.S >= 16 && (unsigned long long)pl.S + w + 2 < 65535);
-                    CHECK((pl.S + w) % sb == 0 || getenv("MZ_FAST_S"));  // whole iterations
-                    CHECK(mz::fast_nb(pl.S, w) < 2048);
-                    CHECK(mz::fast_smem(pl.S, w, pl.list_cap) <= mz::FAST_SMEM_LIMIT);
-                    CHECK(pl.list_cap >= 256 && pl.list_cap % 128 == 0);
+                    const unsigned lead = mz::fast_lead(w);
+                    CHECK(lead >= w && lead % wt == 0 && lead < w + wt && pl.lead == lead);
+                    CHECK(pl.S >= 1 && (unsigned long long)pl.S + lead + sb + 2 < 65535);
+                    CHECK(pl.nb == mz::fast_nb(pl.S, w) && pl.nb * sb >= lead + pl.S);
+                    // whole iterations whenever the segment length was free to choose
+                    CHECK((pl.S + lead) % sb == 0 || getenv("MZ_FAST_S") || pl.S < sb);
+                    // queue entries: selected k-mer in 11 bits (u16 entries), window end - k-mer in 5 / 8 bits
+                    CHECK(w > 32 || pl.nb * sb + 1 < 2048);
+                    CHECK(w <= 32 ? mz::fast_qbytes(w) == 2 : mz::fast_qbytes(w) == 4);
+                    CHECK(pl.q_rows == pl.q_trig + (w > 32 ? 4 : sb) && pl.q_trig >= 1);  // guard rows between two overflow checks
+                    CHECK(mz::fast_smem(w, pl.q_rows) <= mz::FAST_SMEM_LIMIT);
                     CHECK((unsigned long long)pl.num_tiles * 32 * pl.S >= nwin);
                     CHECK(pl.grid >= 1 && pl.grid <= 148 * mz::FAST_BPS);
-                    CHECK(pl.scratch_words_per_block == mz::fast_scratch_words(pl.S, w));
+                    CHECK(pl.scratch_words_per_block == mz::fast_spill_words(pl.S, w));
+                    // the spill area holds every entry a lane can push in a tile
+                    CHECK(pl.scratch_words_per_block * 4 >= (size_t)pl.nb * sb * 32 * mz::fast_qbytes(w));
                 }
             }
         }
