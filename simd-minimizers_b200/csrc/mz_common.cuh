@@ -45,6 +45,7 @@ struct KArgs {
     uint64_t r1_words_per_warp;        // fast kernel, w > 32: level-1 result rows per warp (else 0)
     // fast kernel: per-lane emission queues in shared memory (rows of 32 entries, one per lane)
     uint32_t q_rows;                   // rows per warp and buffer (q_trig + one loop iteration of guard rows)
+    uint32_t q_bufs;                   // queue buffers per warp: 2 = emission deferred by one tile, 1 = right away
     uint32_t q_trig;                   // a lane holding more rows than this at the end of an iteration spills the warp's queues
     uint32_t nb;                       // loop iterations per tile (the same for every lane)
     uint32_t lead;                     // elements in front of the first valid window end

@@ -94,13 +94,23 @@ inline size_t fast_spill_words(uint32_t S, uint32_t w) {
     return (size_t)fast_nb(S, w) * fast_sb(fast_wt(w)) * 32 * fast_qbytes(w) / 4;
 }
 // shared memory: table | misc | per warp: lane offsets (2 tiles in flight) | queues (2 tiles in flight)
-inline size_t fast_smem(uint32_t w, uint32_t q_rows) {
+inline size_t fast_smem(uint32_t w, uint32_t q_rows, uint32_t q_bufs = 2) {
     return 256 * FAST_TC * 16 + 64 +
-           (size_t)FAST_WARPS * (2 * FAST_TOFFS * 4 + 2 * (size_t)q_rows * 32 * fast_qbytes(w));
+           (size_t)FAST_WARPS * (2 * FAST_TOFFS * 4 + (size_t)q_bufs * q_rows * 32 * fast_qbytes(w));
 }
 inline double fast_density(const mz_params& p) {
     return p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
          : p.mode == MZ_MODE_CLOSED_SYNCMER ? (p.w == 1 ? 1.0 : 2.0 / p.w) : 1.0 / p.w;
+}
+// Queue buffers per warp.  Two: the look-back + emission of a tile is deferred until the warp's
+// next tile has been computed (its predecessors have published by then).  One, for dense outputs
+// (more than about one window in six emits: measured cross-over, w <= 10): the queues then hold twice the segment length, which
+// halves the (k + w - 2)-base warm-up per window; the emission pass is long enough there that
+// waiting for the predecessors costs less than that.
+inline uint32_t fast_q_bufs(const mz_params& p) {
+    static const int force = getenv("MZ_FAST_NBUF") ? atoi(getenv("MZ_FAST_NBUF")) : 0;
+    if (force == 1 || force == 2) return (uint32_t)force;
+    return fast_density(p) >= 0.175 ? 1u : 2u;
 }
 // rows a lane may hold before the warp spills: expected entries of a segment + 6 sigma-ish slack
 inline uint32_t fast_q_trig(uint32_t S, const mz_params& p) {
@@ -202,6 +212,40 @@ __device__ __forceinline__ void q_push_ne_fma(uint32_t& qa, uint32_t a, uint32_t
                      "@p st.shared.u16 [%0], lo;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t}"
                      : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "r"(rowb), "r"(one));
 }
+// Up to four consecutive windows in one go (NG of them): entry u is pushed when its selection r[u]
+// differs from the one before it (prev, r[0], r[1], r[2]).  One asm block, so that the queue
+// pointer stays in one register across the four predicated bumps.
+template <bool WIDE, int NG>
+__device__ __forceinline__ void q_push4_ne_fma(uint32_t& qa, uint32_t prev, const uint32_t (&r)[4], const uint32_t (&e)[4],
+                                               uint32_t rowb, uint32_t one) {
+    if constexpr (WIDE) {
+        asm volatile(
+            "{\n\t.reg .pred p0, p1, p2, p3;\n\t"
+            "setp.ne.u32 p0, %1, %9;\n\tsetp.ne.u32 p1, %2, %1;\n\tsetp.ne.u32 p2, %3, %2;\n\tsetp.ne.u32 p3, %4, %3;\n\t"
+            "@p0 st.shared.u32 [%0], %5;\n\t@p0 mad.lo.u32 %0, %10, %11, %0;\n\t"
+            "@p1 st.shared.u32 [%0], %6;\n\t@p1 mad.lo.u32 %0, %10, %11, %0;\n\t"
+            "@p2 st.shared.u32 [%0], %7;\n\t@p2 mad.lo.u32 %0, %10, %11, %0;\n\t"
+            "@p3 st.shared.u32 [%0], %8;\n\t@p3 mad.lo.u32 %0, %10, %11, %0;\n\t}"
+            : "+r"(qa)
+            : "r"(r[0]), "r"(NG > 1 ? r[1] : r[0]), "r"(NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0])),
+              "r"(NG > 3 ? r[3] : (NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0]))), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]),
+              "r"(prev), "r"(rowb), "r"(one));
+    } else {
+        asm volatile(
+            "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b16 l0, l1, l2, l3;\n\t"
+            "setp.ne.u32 p0, %1, %9;\n\tsetp.ne.u32 p1, %2, %1;\n\tsetp.ne.u32 p2, %3, %2;\n\tsetp.ne.u32 p3, %4, %3;\n\t"
+            "cvt.u16.u32 l0, %5;\n\tcvt.u16.u32 l1, %6;\n\tcvt.u16.u32 l2, %7;\n\tcvt.u16.u32 l3, %8;\n\t"
+            "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %10, %11, %0;\n\t"
+            "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %10, %11, %0;\n\t"
+            "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %10, %11, %0;\n\t"
+            "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %10, %11, %0;\n\t}"
+            : "+r"(qa)
+            : "r"(r[0]), "r"(NG > 1 ? r[1] : r[0]), "r"(NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0])),
+              "r"(NG > 3 ? r[3] : (NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0]))), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]),
+              "r"(prev), "r"(rowb), "r"(one));
+    }
+}
+
 // entry at shared address `addr`
 template <bool WIDE>
 __device__ __forceinline__ uint32_t q_load(uint32_t addr) {
@@ -457,7 +501,8 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
     const uint32_t QROWS = a.q_rows;
     // this warp's lane offsets and queues, two tiles in flight
     uint32_t* const tp0 = misc + 16 + warp * (2 * FAST_TOFFS);
-    unsigned char* const q0 = reinterpret_cast<unsigned char*>(misc + 16 + FAST_WARPS * 2 * FAST_TOFFS) + (size_t)warp * 2 * QROWS * ROWB;
+    const bool defer = a.q_bufs == 2;  // look-back + emission one tile later (two queue buffers)
+    unsigned char* const q0 = reinterpret_cast<unsigned char*>(misc + 16 + FAST_WARPS * 2 * FAST_TOFFS) + (size_t)warp * a.q_bufs * QROWS * ROWB;
     const uint32_t q0s = (uint32_t)__cvta_generic_to_shared(q0) + lane * (uint32_t)sizeof(QT);
     const uint32_t Wr = XW ? a.w : (uint32_t)W;  // real window length
     const uint32_t lead = a.lead, NB = a.nb;
@@ -509,7 +554,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
 
     // Software pipeline over tiles: the look-back + emission of tile A runs after the main loop
     // of the next tile B, so A's predecessors have published their counts by then.
-    uint32_t p_valid = 0, p_tile = 0, p_cnt = 0, p_inc = 0, p_spilled = 0, cur = 0;
+    uint32_t p_valid = 0, p_tile = 0, p_inc = 0, p_spilled = 0, cur = 0;
     for (;;) {  // persistent: one tile (32 threads x S windows) per iteration, per warp
         uint32_t tile = 0;
         if (lane == 0) tile = atomicAdd(a.ticket, 1u);
@@ -773,16 +818,23 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                                 gr[0] = f.x, gr[1] = f.y, gr[2] = f.z, gr[3] = f.w;
                             }
                         }
+                        if (!SYNC && !AMB) {
+                            uint32_t ge[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            if (u >= ng) continue;
-                            const int tt = o + g0 + u;            // window inside the iteration
-                            const uint32_t r = gr[u], ps = gp[u];
-                            const uint32_t ent = XW ? imad(r & 0xffffu, DMUL, ps) : imad(r, DMUL, ps);
-                            if (!SYNC && !AMB) {
-                                q_push_ne_fma<XW>(qa, r, prev, ent, rowb, one);
-                                prev = r;
-                            } else {
+                            for (int u = 0; u < 4; u++)
+                                ge[u] = u < ng ? (XW ? imad(gr[u] & 0xffffu, DMUL, gp[u]) : imad(gr[u], DMUL, gp[u])) : 0u;
+                            if (ng == 4) q_push4_ne_fma<XW, 4>(qa, prev, gr, ge, rowb, one);
+                            else if (ng == 3) q_push4_ne_fma<XW, 3>(qa, prev, gr, ge, rowb, one);
+                            else if (ng == 2) q_push4_ne_fma<XW, 2>(qa, prev, gr, ge, rowb, one);
+                            else q_push4_ne_fma<XW, 1>(qa, prev, gr, ge, rowb, one);
+                            prev = gr[ng - 1];
+                        } else {
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                if (u >= ng) continue;
+                                const int tt = o + g0 + u;            // window inside the iteration
+                                const uint32_t r = gr[u], ps = gp[u];
+                                const uint32_t ent = XW ? imad(r & 0xffffu, DMUL, ps) : imad(r, DMUL, ps);
                                 bool pe;
                                 if (SYNC) {
                                     const uint32_t d = ps - (r & 0xffffu);
@@ -852,9 +904,11 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
         if (lane == 31) tp[32] = inc;
         }  // have
 
-        // ---- ordered emission of the PREVIOUS tile, warp-autonomous (no block barriers) --------
+        // ---- ordered emission of the PREVIOUS tile (of this one without a second queue buffer),
+        //      warp-autonomous (no block barriers) ---------------------------------------------------
+        if (!defer) p_valid = have ? 1u : 0u, p_tile = tile, p_inc = inc, p_spilled = tile_spilled;
         if (p_valid) {
-        const uint32_t tile_e = p_tile, inc_e = p_inc, pb = cur ^ 1u;
+        const uint32_t tile_e = p_tile, inc_e = p_inc, pb = defer ? (cur ^ 1u) : 0u;
         const uint32_t total = __shfl_sync(0xffffffffu, inc_e, 31);
         const unsigned long long gbase = lookback_excl(a.tile_state, tile_e, total);
         if (lane == 0 && tile_e == a.num_tiles - 1) {
@@ -894,15 +948,16 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
         }
         }  // p_valid
         if (!have) break;
-        p_valid = 1, p_tile = tile, p_cnt = cnt, p_inc = inc, p_spilled = tile_spilled;
-        (void)p_cnt;
-        cur ^= 1u;
+        if (defer) {
+            p_valid = 1, p_tile = tile, p_inc = inc, p_spilled = tile_spilled;
+            cur ^= 1u;
+        }
     }
 }
 
 // ---- host side ---------------------------------------------------------------------------
 struct FastPlan {
-    uint32_t S = 0, num_tiles = 0, grid = 0, q_rows = 0, q_trig = 0, nb = 0, lead = 0;
+    uint32_t S = 0, num_tiles = 0, grid = 0, q_rows = 0, q_trig = 0, q_bufs = 2, nb = 0, lead = 0;
     size_t scratch_words_per_block = 0;  // spill area, per warp and buffer
     size_t r1_words = 0;                 // XW: level-1 rows, per warp
 };
@@ -922,7 +977,8 @@ inline bool fast_queue_plan(uint32_t S, const mz_params& p, FastPlan* pl) {
     // entry field widths: selected k-mer below 2^11 (u16 entries) / 2^16 (positions in the keys)
     const uint32_t elems = pl->nb * sb + 1;
     if (p.w <= FAST_MAX_W ? elems >= 2048 : elems >= 65535) return false;
-    return fast_smem(p.w, pl->q_rows) <= FAST_SMEM_LIMIT;
+    pl->q_bufs = fast_q_bufs(p);
+    return fast_smem(p.w, pl->q_rows, pl->q_bufs) <= FAST_SMEM_LIMIT;
 }
 
 // Geometry for the fast kernel; returns false when (k, w, ...) is outside its domain.
@@ -976,6 +1032,7 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
 inline void fast_plan_args(const FastPlan& fp, KArgs& a) {
     a.S = fp.S;
     a.q_rows = fp.q_rows;
+    a.q_bufs = fp.q_bufs;
     a.q_trig = fp.q_trig;
     a.nb = fp.nb;
     a.lead = fp.lead;
@@ -987,7 +1044,7 @@ inline void fast_plan_args(const FastPlan& fp, KArgs& a) {
 template <int W, bool HC, bool LR, bool SYNC, bool AMB = false, bool XW = false>
 inline int launch_fast_inst(uint32_t grid, const KArgs& a, cudaStream_t st) {
     auto kern = mz_fast_kernel<W, HC, LR, SYNC, AMB, XW>;
-    const size_t smem = fast_smem(a.w, a.q_rows);
+    const size_t smem = fast_smem(a.w, a.q_rows, a.q_bufs);
     if (smem > 48 * 1024 &&
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         return MZ_ERR_CUDA;

@@ -10,7 +10,7 @@ cfg = bench.CONFIGS[sys.argv[1] if len(sys.argv) > 1 else "c2"]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else cfg["n"]
 ndev = torch.cuda.device_count()
 host, off = bench.synth_packed_range(bench.SEED, 0, n)
-pin = torch.empty(host.size, dtype=torch.uint8).pin_memory(); pin.numpy()[:] = host; del host
+pin = bench.HostBuf(L, ffi, host.size, np.uint8); pin.np[:host.size] = host; del host
 k, w = cfg["k"], cfg["w"]
 p = ffi.MzParams()
 (L.mz_params_mulhash if cfg["hasher"] == "mul" else L.mz_params_nthash)(C.byref(p), k, w, cfg["mode"], int(cfg["canonical"]))
@@ -18,9 +18,9 @@ p.want_sk, p.value_bits = cfg["want_sk"], cfg["value_bits"]
 vw = cfg["value_bits"] // 64
 dens = 2.0 / (w + 1) if cfg["mode"] == 0 else 2.0 / w
 cap = int(n * dens * 1.1) + 65536
-h_pos = torch.empty(cap, dtype=torch.int32).pin_memory()
-h_sk = torch.empty(cap if cfg["want_sk"] else 1, dtype=torch.int32).pin_memory()
-h_val = torch.empty(max(cap * vw, 1), dtype=torch.int64).pin_memory()
+h_pos = bench.HostBuf(L, ffi, cap * 4, np.uint32)
+h_sk = bench.HostBuf(L, ffi, (cap if cfg["want_sk"] else 1) * 4, np.uint32)
+h_val = bench.HostBuf(L, ffi, max(cap * vw, 1) * 8, np.uint64)
 sets = [list(range(m)) for m in (1, 2, 4, 8) if m <= ndev]
 ref = None
 for devs in sets:
@@ -34,11 +34,11 @@ for devs in sets:
         os.environ.update(env)
         ts = []
         for it in range(4):
-            out = ffi.MzOut(h_pos.data_ptr(), h_sk.data_ptr() if cfg["want_sk"] else None, h_val.data_ptr() if vw else None, cap, 0)
+            out = ffi.MzOut(h_pos.ptr, h_sk.ptr if cfg["want_sk"] else None, h_val.ptr if vw else None, cap, 0)
             t0 = time.perf_counter()
-            ffi.check(L.mz_run(ctx.handle, C.byref(p), pin.data_ptr(), off, n, C.byref(out)))
+            ffi.check(L.mz_run(ctx.handle, C.byref(p), pin.ptr, off, n, C.byref(out)))
             ts.append((time.perf_counter() - t0) * 1e3)
-        cs = (int(out.count), int(h_pos.numpy()[:out.count].astype(np.uint64).sum()), int(h_val.numpy()[:out.count * vw].view(np.uint64).sum()) if vw else 0)
+        cs = (int(out.count), int(h_pos.np[:out.count].astype(np.uint64).sum()), int(h_val.np[:out.count * vw].sum()) if vw else 0)
         if ref is None:
             ref = cs
         assert cs == ref, (cs, ref)
