@@ -217,6 +217,26 @@ int mz_values(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t b
               const uint32_t* pos, uint64_t n_pos, uint32_t value_bits, uint64_t* val_out);
 
 /*
+ * mz_run_bucket_stats -- the path plus a first consumer that stays on the device.
+ * A super-k-mer is a maximal run of windows with the same minimizer (bench/src/minimizer.rs:3-36,
+ * "Problem C"; the i-th one starts at window sk[i] of a `.super_kmers()` run, src/lib.rs:339-352,
+ * and ends where the next one starts).  Tools downstream of a minimizer scan shard super-k-mers by
+ * their minimizer; this call does that sharding where the minimizers are, in HBM, and returns only
+ * the histograms: for every bucket b < n_buckets (<= 16384)
+ *     superkmers_out[b] = super-k-mers whose minimizer falls into b,
+ *     windows_out[b]    = windows covered by them (sum over b = n_bp - l + 1),
+ * with bucket = floor(mix64(value) * n_buckets / 2^64), value = the minimizer's k-mer as
+ * values_u64() reports it (canonical builders: min(kmer, revcomp)), mix64 = the splitmix64 finaliser
+ * (x += 0x9E3779B97F4A7C15; x = (x ^ x>>30) * 0xBF58476D1CE4E5B9; x = (x ^ x>>27) * 0x94D049BB133111EB;
+ * x ^ x>>31).  Minimizer builders with k <= 32 only.  Nothing but the packed input (host -> device)
+ * and 16 * n_buckets bytes (device -> host) crosses the bus; all devices of the context take chunks.
+ * Equivalent to running mz_run with want_sk = 1, value_bits = 64 and building the histograms on
+ * the host, which moves 16 bytes per minimizer over PCIe instead.
+ */
+int mz_run_bucket_stats(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset, uint64_t n_bp,
+                        uint32_t n_buckets, uint64_t* superkmers_out, uint64_t* windows_out, uint64_t* n_minimizers);
+
+/*
  * mz_pcie_probe -- measured host <-> device copy rate of the context's devices, all of them at
  * the same time (pinned host memory, `reps` copies of `bytes_per_device` per device and
  * direction).  This is the ceiling of every end-to-end number of mz_run / mz_run_batch: one PCIe

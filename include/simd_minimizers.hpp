@@ -13,6 +13,7 @@
 #include <memory>
 #include <stdexcept>
 #include <string>
+#include <utility>
 #include <vector>
 
 #include "mz_b200.h"
@@ -36,12 +37,21 @@ struct PackedNSeq {
     PackedNSeq slice(uint64_t b, uint64_t e) const { return {seq.slice(b, e), ambiguous, amb_offset + b}; }
 };
 
-struct Hasher {  // seq-hash NtHasher<RC> / MulHasher<RC>
-    enum Kind { Nt, Mul } kind = Nt;
+struct Hasher {  // seq-hash NtHasher<RC> / MulHasher<RC>, or any per-base table hasher (seeded ones)
+    enum Kind { Nt, Mul, Tables } kind = Nt;
     uint32_t k = 0;
     bool canonical = true;
+    uint32_t f[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0}, rot = 7;
     static Hasher nt(uint32_t k, bool rc = true) { return {Nt, k, rc}; }
     static Hasher mul(uint32_t k, bool rc = true) { return {Mul, k, rc}; }
+    // `H::new_with_seed(k, seed)` (src/lib.rs:157): seq-hash derives per-base tables from the seed;
+    // pass those tables (indexed by packed code A=0 C=1 T=2 G=3)
+    static Hasher tables(uint32_t k, const uint32_t (&f)[4], const uint32_t (&c)[4], uint32_t rot = 7, bool rc = true) {
+        Hasher h{Tables, k, rc};
+        for (int b = 0; b < 4; b++) h.f[b] = f[b], h.c[b] = c[b];
+        h.rot = rot;
+        return h;
+    }
     bool is_canonical() const { return canonical; }
 };
 
@@ -64,19 +74,38 @@ inline mz_ctx* thread_ctx() {  // thread_local scratch, like src/lib.rs:217-219
 }
 }  // namespace detail
 
+// src/lib.rs:232-237, 579-630.  Values are lazy, as in the reference: run() moves positions only,
+// values_*() computes the k-mers (l-mers for syncmers) of ALL of min_pos on the device (mz_values;
+// the sequence of the run is still resident there).
 class Output {
 public:
-    Output(uint32_t len, std::vector<uint64_t> v, const std::vector<uint32_t>* p) : len_(len), vals_(std::move(v)), pos_(p) {}
+    Output(uint32_t len, mz_params p, PackedSeq seq, const std::vector<uint32_t>* pos) : len_(len), p_(p), seq_(seq), pos_(pos) {}
     uint32_t len() const { return len_; }  // k for minimizers, k+w-1 for syncmers
-    const std::vector<uint64_t>& values_u64() const {
-        if (len_ > 32) throw std::invalid_argument(mz_strerror(MZ_ERR_VALUE_WIDTH));
-        return vals_;
+    std::vector<uint64_t> values_u64() const {
+        std::vector<uint64_t> v(pos_->size());
+        detail::check(mz_values(detail::thread_ctx(), &p_, seq_.data, seq_.offset, seq_.len, pos_->data(), pos_->size(), 64, v.data()));
+        return v;
+    }
+    // (lo, hi) pairs
+    std::vector<std::pair<uint64_t, uint64_t>> values_u128() const {
+        std::vector<uint64_t> raw(2 * pos_->size());
+        detail::check(mz_values(detail::thread_ctx(), &p_, seq_.data, seq_.offset, seq_.len, pos_->data(), pos_->size(), 128, raw.data()));
+        std::vector<std::pair<uint64_t, uint64_t>> v(pos_->size());
+        for (size_t i = 0; i < v.size(); i++) v[i] = {raw[2 * i], raw[2 * i + 1]};
+        return v;
+    }
+    std::vector<std::pair<uint32_t, uint64_t>> pos_and_values_u64() const {
+        const auto vals = values_u64();
+        std::vector<std::pair<uint32_t, uint64_t>> v(vals.size());
+        for (size_t i = 0; i < v.size(); i++) v[i] = {(*pos_)[i], vals[i]};
+        return v;
     }
     const std::vector<uint32_t>& positions() const { return *pos_; }
 
 private:
     uint32_t len_;
-    std::vector<uint64_t> vals_;
+    mz_params p_;
+    PackedSeq seq_;
     const std::vector<uint32_t>* pos_;
 };
 
@@ -98,14 +127,24 @@ public:
     }
     // Appends to min_pos (and to the super-k-mer vector), src/lib.rs:80-81.
     Output run(const PackedSeq& seq, std::vector<uint32_t>& min_pos) const {
-        return run_impl(seq, nullptr, 0, min_pos);
+        return run_impl(seq, nullptr, 0, min_pos, /*scalar=*/false);
+    }
+    // run_scalar (src/lib.rs:372-378, 508-533): same result; the scalar collectors overwrite the
+    // vectors from index 0 (src/collect.rs:15-76) instead of appending.
+    Output run_scalar(const PackedSeq& seq, std::vector<uint32_t>& min_pos) const {
+        return run_impl(seq, nullptr, 0, min_pos, /*scalar=*/true);
+    }
+    std::vector<uint32_t> run_scalar_once(const PackedSeq& seq) const {
+        std::vector<uint32_t> v;
+        run_scalar(seq, v);
+        return v;
     }
     // src/lib.rs:451-496: windows holding an ambiguous base produce nothing.  Canonical builders
     // without super-k-mers only (a type-state restriction in the reference, checked here).
     Output run_skip_ambiguous_windows(const PackedNSeq& nseq, std::vector<uint32_t>& min_pos) const {
         if (!canonical_ || sk_) throw std::logic_error("run_skip_ambiguous_windows: canonical builder without super_kmers() only");
         if (!nseq.ambiguous) throw std::invalid_argument("PackedNSeq without an ambiguity mask");
-        return run_impl(nseq.seq, nseq.ambiguous, nseq.amb_offset, min_pos);
+        return run_impl(nseq.seq, nseq.ambiguous, nseq.amb_offset, min_pos, false);
     }
     std::vector<uint32_t> run_skip_ambiguous_windows_once(const PackedNSeq& nseq) const {
         std::vector<uint32_t> v;
@@ -117,29 +156,43 @@ public:
         run(seq, v);
         return v;
     }
+    // Not in the reference crate: super-k-mers (bench/src/minimizer.rs:3-36) sharded by their
+    // minimizer on the device; only the two histograms leave the GPU (mz_run_bucket_stats).
+    void bucket_stats(const PackedSeq& seq, uint32_t n_buckets, std::vector<uint64_t>& superkmers,
+                      std::vector<uint64_t>& windows, uint64_t* n_minimizers = nullptr) const {
+        if (syncmer_) throw std::logic_error("bucket_stats() is only available for minimizers");
+        const mz_params p = params();
+        superkmers.assign(n_buckets, 0);
+        windows.assign(n_buckets, 0);
+        detail::check(mz_run_bucket_stats(detail::thread_ctx(), &p, seq.data, seq.offset, seq.len, n_buckets,
+                                          superkmers.data(), windows.data(), n_minimizers));
+    }
 
 private:
-    Output run_impl(const PackedSeq& seq, const uint8_t* amb, uint64_t amb_off, std::vector<uint32_t>& min_pos) const {
+    mz_params params() const {
         mz_params p;
         detail::check(mz_params_nthash(&p, k_, w_, syncmer_, canonical_));
         if (has_hasher_) {
             if (hasher_.k != k_) throw std::invalid_argument("hasher.k() must equal k");
-            detail::check(hasher_.kind == Hasher::Nt ? mz_params_set_nthash(&p, hasher_.canonical)
-                                                    : mz_params_set_mulhash(&p, hasher_.canonical));
+            detail::check(hasher_.kind == Hasher::Nt    ? mz_params_set_nthash(&p, hasher_.canonical)
+                          : hasher_.kind == Hasher::Mul ? mz_params_set_mulhash(&p, hasher_.canonical)
+                                                        : mz_params_set_tables(&p, hasher_.f, hasher_.c, hasher_.rot, hasher_.canonical));
         }
-        const uint32_t len = syncmer_ ? k_ + w_ - 1 : k_;
         p.want_sk = sk_ != nullptr;
-        p.value_bits = len <= 32 ? 64 : 0;
+        p.value_bits = 0;  // positions only; values are lazy (Output)
+        return p;
+    }
+    Output run_impl(const PackedSeq& seq, const uint8_t* amb, uint64_t amb_off, std::vector<uint32_t>& min_pos, bool scalar) const {
+        const mz_params p = params();
+        const uint32_t len = syncmer_ ? k_ + w_ - 1 : k_;
         detail::check(mz_params_validate(&p, seq.len));
         const uint64_t l = k_ + w_ - 1, nwin = seq.len >= l ? seq.len - l + 1 : 0;
         uint64_t cap = (uint64_t)(nwin * 2.5 / (w_ + 1.0)) + 4096;
         std::vector<uint32_t> pos, sk;
-        std::vector<uint64_t> val;
         for (;;) {
             pos.resize(cap);
             if (sk_) sk.resize(cap);
-            if (p.value_bits) val.resize(cap);
-            mz_out out{pos.data(), sk_ ? sk.data() : nullptr, p.value_bits ? val.data() : nullptr, cap, 0};
+            mz_out out{pos.data(), sk_ ? sk.data() : nullptr, nullptr, cap, 0};
             int rc = amb ? mz_run_skip_ambiguous(detail::thread_ctx(), &p, seq.data, seq.offset, seq.len, amb, amb_off, &out)
                          : mz_run(detail::thread_ctx(), &p, seq.data, seq.offset, seq.len, &out);
             if (rc == MZ_ERR_CAPACITY) {
@@ -149,15 +202,20 @@ private:
             detail::check(rc);
             pos.resize(out.count);
             if (sk_) sk.resize(out.count);
-            if (p.value_bits) val.resize(out.count);
             break;
         }
-        // SIMD-collector quirk (src/collect.rs:257,267)
-        size_t skip = (!syncmer_ && !pos.empty() && !min_pos.empty() && pos[0] == min_pos.back()) ? 1 : 0;
-        min_pos.insert(min_pos.end(), pos.begin() + skip, pos.end());
-        if (sk_) sk_->insert(sk_->end(), sk.begin() + skip, sk.end());
-        if (skip && !val.empty()) val.erase(val.begin());
-        return Output(len, std::move(val), &min_pos);
+        if (scalar) {  // overwrite; an empty window stream leaves the index vector untouched (src/collect.rs:45-48)
+            min_pos = pos;
+            if (sk_ && nwin) *sk_ = sk;
+        } else {
+            // SIMD-collector quirk (src/collect.rs:257,267)
+            size_t skip = (!syncmer_ && !pos.empty() && !min_pos.empty() && pos[0] == min_pos.back()) ? 1 : 0;
+            min_pos.insert(min_pos.end(), pos.begin() + skip, pos.end());
+            if (sk_) sk_->insert(sk_->end(), sk.begin() + skip, sk.end());
+        }
+        mz_params pv = p;
+        pv.want_sk = 0;
+        return Output(len, pv, seq, &min_pos);
     }
 
     uint32_t k_, w_;

@@ -535,6 +535,22 @@ class Builder:
         metric).  Returns (pos, sk, vals); u128 values come as an (n, 2) array of (lo, hi)."""
         return self._execute(seq, value_bits, skip=skip_ambiguous)
 
+    def bucket_stats(self, seq, n_buckets: int):
+        """Not in the reference crate: super-k-mers (bench/src/minimizer.rs:3-36) sharded by their
+        minimizer on the device (mz_run_bucket_stats).  Returns (superkmers[n_buckets],
+        windows[n_buckets], n_minimizers); only the histograms leave the GPU."""
+        if self.syncmer != 0:
+            raise TypeError("bucket_stats() is only available for minimizers")
+        seq = seq.as_slice()
+        p = self._params(0)
+        ctx = self._ctx or default_context()
+        cnt = np.zeros(n_buckets, dtype=np.uint64)
+        win = np.zeros(n_buckets, dtype=np.uint64)
+        total = C.c_uint64(0)
+        _check(_ffi.lib().mz_run_bucket_stats(ctx.handle, C.byref(p), seq.data.ctypes.data, seq.offset, seq.len,
+                                              n_buckets, cnt.ctypes.data, win.ctypes.data, C.byref(total)))
+        return cnt, win, int(total.value)
+
     def run_skip_ambiguous_windows(self, nseq, min_pos: U32Vec) -> Output:
         """src/lib.rs:451-496: windows containing an ambiguous base produce nothing.  ``nseq`` is
         a PackedNSeq(Vec), or an AsciiSeq (packed and masked on the device).  Canonical builders

@@ -30,7 +30,7 @@ SYMBOLS = [
     "mz_ctx_create", "mz_ctx_destroy", "mz_ctx_device_count", "mz_host_alloc", "mz_host_free",
     "mz_run", "mz_run_device", "mz_run_batch", "mz_pack_ascii", "mz_run_ascii", "mz_last_timing",
     "mz_run_skip_ambiguous", "mz_run_device_skip_ambiguous", "mz_pack_ascii_n",
-    "mz_run_ascii_skip_ambiguous", "mz_params_set_tables", "mz_values", "mz_pcie_probe", "mz_alu_probe",
+    "mz_run_ascii_skip_ambiguous", "mz_params_set_tables", "mz_values", "mz_pcie_probe", "mz_alu_probe", "mz_run_bucket_stats",
 ]
 
 
@@ -117,6 +117,9 @@ def lib():
                                        C.c_uint32, C.c_uint32]
     L.mz_values.argtypes = [vp, C.POINTER(MzParams), vp, C.c_uint64, C.c_uint64, vp, C.c_uint64,
                             C.c_uint32, vp]
+    if not os.environ.get("MZ_B200_LIB") or hasattr(L, "mz_run_bucket_stats"):  # (older A/B variants lack it)
+        L.mz_run_bucket_stats.argtypes = [vp, C.POINTER(MzParams), vp, C.c_uint64, C.c_uint64, C.c_uint32, vp, vp,
+                                          C.POINTER(C.c_uint64)]
     L.mz_alu_probe.argtypes = [vp, C.c_int, C.POINTER(MzAluResult)]
     L.mz_pcie_probe.argtypes = [vp, C.c_uint64, C.c_uint32, C.POINTER(MzPcieResult)]
     _lib = L

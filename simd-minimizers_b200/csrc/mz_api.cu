@@ -118,7 +118,7 @@ void parallel_memcpy(void* dst, const void* src, size_t bytes, unsigned max_thre
         return;
     }
     std::vector<std::thread> th;
-    const size_t per = (bytes / nt + 4095) & ~size_t(4095);
+    const size_t per = ((bytes + nt - 1) / nt + 4095) & ~size_t(4095);  // nt * per >= bytes
     for (unsigned i = 0; i < nt; i++) {
         const size_t b = std::min(bytes, (size_t)i * per), e = std::min(bytes, b + per);
         if (e > b) th.emplace_back([=] { memcpy((char*)dst + b, (const char*)src + b, e - b); });
@@ -155,6 +155,9 @@ struct DevState {
     PinBuf st_offs;                               // batch: chunk-local CSR offsets on their way out
     DevBuf<uint8_t> delta;                        // delta-coded pos / sk of a chunk (transfer codec)
     PinBuf st_delta;
+    // on-device consumer (mz_run_bucket_stats): per-device histograms and per-chunk seam records
+    DevBuf<unsigned long long> hist;
+    PinBuf st_tail;
     // front-loaded uploads of the chunk pipelines (slot 0 of a device only): the device's whole
     // share of the input, copied on its own stream as early as the link allows
     DevBuf<uint8_t> in_all;
@@ -841,6 +844,222 @@ __global__ void mz_values_kernel(mz::KArgs a, const uint32_t* __restrict__ pos, 
     }
 }
 
+// ---- first on-device consumer: super-k-mers bucketed by their minimizer -------------
+// A super-k-mer is a maximal run of windows with the same minimizer (bench/src/minimizer.rs:3-36,
+// Problem C): entry i of a .super_kmers() run starts at window sk[i] and ends where entry i+1
+// starts.  Downstream tools (k-mer counters, partitioned assemblers, sparse dictionaries) shard
+// super-k-mers by minimizer: bucket = floor(mix64(value) * n_buckets / 2^64), mix64 = the
+// splitmix64 finaliser, value = the canonical k-mer of the minimizer (values_u64).  The kernel
+// below consumes a chunk's (sk, val) arrays where the minimizer kernel left them, in HBM, and
+// adds to per-device histograms: super-k-mers per bucket and windows per bucket.
+__host__ __device__ inline uint64_t mz_mix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+struct ChunkTail {  // what the host needs to stitch the chunk seams
+    unsigned long long count;  // entries of the chunk
+    uint32_t first_sk;         // first window that starts a super-k-mer inside the chunk
+    uint32_t last_bucket;      // bucket of the chunk's last super-k-mer (it runs on into the next chunk)
+};
+constexpr uint32_t kBucketMax = 16384;  // two u32 counters per bucket in shared memory
+__global__ void __launch_bounds__(1024, 1)
+mz_bucket_kernel(const uint32_t* __restrict__ sk, const uint64_t* __restrict__ val, const unsigned long long* count_ptr,
+                 const uint32_t* overflow, uint32_t wend, uint32_t nb, unsigned long long* g_cnt,
+                 unsigned long long* g_win, ChunkTail* tail) {
+    extern __shared__ uint32_t hs[];  // [nb] super-k-mers, [nb] windows
+    if (*overflow) return;            // the chunk is re-run with the exact capacity first
+    const unsigned long long n = *count_ptr;
+    for (uint32_t i = threadIdx.x; i < 2 * nb; i += blockDim.x) hs[i] = 0;
+    __syncthreads();
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const uint32_t b = (uint32_t)__umul64hi(mz_mix64(val[i]), (uint64_t)nb);
+        const uint32_t next = i + 1 < n ? sk[i + 1] : wend;
+        atomicAdd(&hs[b], 1u);
+        atomicAdd(&hs[nb + b], next - sk[i]);
+        if (i + 1 == n) tail->last_bucket = b;
+        if (i == 0) tail->first_sk = sk[0];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) tail->count = n;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < nb; i += blockDim.x) {
+        if (hs[i]) atomicAdd(&g_cnt[i], (unsigned long long)hs[i]);
+        if (hs[nb + i]) atomicAdd(&g_win[i], (unsigned long long)hs[nb + i]);
+    }
+}
+
+// Chunk pipeline of the consumer: front-loaded uploads, minimizer kernel, bucket kernel; only the
+// seam records (16 bytes per chunk) and, at the end, the histograms cross the bus.
+int run_bucket_stats(mz_ctx* ctx, const mz_params& p, const uint8_t* packed, uint64_t bp_offset, uint64_t n_bp,
+                     uint32_t nb, uint64_t* cnt_out, uint64_t* win_out, uint64_t* total_out) {
+    const uint32_t l = p.k + p.w - 1;
+    const uint64_t nwin = n_bp - l + 1;
+    const size_t ndev = ctx->devs.size();
+    const uint64_t ND = ndev;
+    uint64_t chunk = std::max<uint64_t>(1ull << 22, (nwin + std::max<uint64_t>(24, 6 * ndev) - 1) / std::max<uint64_t>(24, 6 * ndev));
+    if (const char* e = getenv("MZ_CHUNK_WINDOWS")) chunk = std::max<uint64_t>(1, strtoull(e, nullptr, 10));
+    const uint64_t nchunks = (nwin + chunk - 1) / chunk;
+    struct Job {
+        uint64_t wb, we, cap, byte_lo;
+        size_t nbytes;
+        const uint8_t* d_in = nullptr;
+        cudaEvent_t up_done = nullptr;
+    };
+    std::vector<Job> jobs(nchunks);
+    auto dev_of = [&](uint64_t c) { return (size_t)(c % ND); };
+    auto slot_of = [&](uint64_t c) { return (int)((c / ND) % kSlots); };
+    struct SyncAll {
+        mz_ctx* ctx;
+        ~SyncAll() {
+            for (size_t i = 0; i < ctx->devs.size(); i++)
+                for (int sl = 0; sl < kSlots; sl++) {
+                    DevState& d = ctx->slot(i, sl);
+                    if (cudaSetDevice(d.device) == cudaSuccess) {
+                        cudaStreamSynchronize(d.stream);
+                        if (sl == 0) cudaStreamSynchronize(d.up);
+                    }
+                }
+            cudaGetLastError();
+            cudaSetDevice(ctx->devs[0].device);
+        }
+    } sync_all{ctx};
+    int rc;
+    const bool page_in = is_pageable(packed);
+    std::vector<size_t> share(ND, 0), off(ND, 0), nth(ND, 0);
+    for (uint64_t c = 0; c < nchunks; c++) {
+        Job& j = jobs[c];
+        j.wb = c * chunk;
+        j.we = std::min<uint64_t>(j.wb + chunk, nwin);
+        j.cap = estimate_capacity(p, j.we - j.wb);
+        const uint64_t blo = j.wb > 0 ? j.wb - 1 : 0;
+        j.byte_lo = (bp_offset + blo) / 4 & ~uint64_t(3);
+        j.nbytes = (bp_offset + j.we + l - 1 + 3) / 4 - j.byte_lo;
+        share[dev_of(c)] += (j.nbytes + 64 + 255) & ~size_t(255);
+    }
+    for (size_t i = 0; i < ndev; i++) {
+        DevState& d0 = ctx->devs[i];
+        CK(cudaSetDevice(d0.device));
+        if ((rc = d0.in_all.reserve(share[i] + 256))) return rc;
+        if ((rc = d0.hist.reserve(2 * (size_t)nb))) return rc;
+        if ((rc = d0.st_tail.reserve(sizeof(ChunkTail) * ((nchunks + ND - 1) / ND + 1)))) return rc;
+        memset(d0.st_tail.p, 0, sizeof(ChunkTail) * ((nchunks + ND - 1) / ND + 1));
+        CK(cudaMemsetAsync(d0.hist.p, 0, 2 * (size_t)nb * 8, d0.up));
+        CK(cudaEventRecord(d0.up_t0, d0.up));
+    }
+    // uploads: pinned input goes up in one sweep; pageable input chunk by chunk through the bounce buffer
+    for (uint64_t c = 0; c < nchunks; c++) {
+        const size_t di = dev_of(c);
+        DevState& d0 = ctx->devs[di];
+        Job& j = jobs[c];
+        CK(cudaSetDevice(d0.device));
+        uint8_t* dst = d0.in_all.p + off[di];
+        off[di] += (j.nbytes + 64 + 255) & ~size_t(255);
+        const uint8_t* src = packed + j.byte_lo;
+        if (page_in) {
+            CK(cudaStreamSynchronize(d0.up));  // the bounce buffer is free again
+            if ((rc = d0.st_in.reserve(j.nbytes))) return rc;
+            parallel_memcpy(d0.st_in.p, src, j.nbytes);
+            src = d0.st_in.p;
+        }
+        CK(cudaMemcpyAsync(dst, src, j.nbytes, cudaMemcpyHostToDevice, d0.up));
+        if ((rc = upload_event(d0, nth[di]++, &j.up_done))) return rc;
+        CK(cudaEventRecord(j.up_done, d0.up));
+        j.d_in = dst;
+    }
+    for (size_t i = 0; i < ndev; i++) {
+        CK(cudaSetDevice(ctx->devs[i].device));
+        CK(cudaEventRecord(ctx->devs[i].up_t1, ctx->devs[i].up));
+    }
+    auto tail_of = [&](uint64_t c) { return reinterpret_cast<ChunkTail*>(ctx->devs[dev_of(c)].st_tail.p) + c / ND; };
+    auto launch = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
+        DevState& d0 = ctx->devs[dev_of(c)];
+        Job& j = jobs[c];
+        int r;
+        if ((r = d.pos.reserve(j.cap))) return r;
+        if ((r = d.sk.reserve(j.cap))) return r;
+        if ((r = d.val.reserve(j.cap))) return r;
+        mz::KArgs a{};
+        fill_input_args(a, p, j.d_in, bp_offset, j.byte_lo, j.nbytes, nwin);
+        a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
+        if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
+        const size_t smem = 2 * (size_t)nb * 4;
+        if (smem > 48 * 1024) CK(cudaFuncSetAttribute(mz_bucket_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ChunkTail* dtail = nullptr;
+        CK(cudaHostGetDevicePointer((void**)&dtail, tail_of(c), 0));
+        mz_bucket_kernel<<<d.sm_count, 1024, smem, d.stream>>>(d.sk.p, d.val.p, d.scratch.p, reinterpret_cast<uint32_t*>(d.scratch.p + 1) + 1,
+                                                             (uint32_t)j.we, nb, d0.hist.p, d0.hist.p + nb, dtail);
+        CK(cudaGetLastError());
+        ctx->timing.kernel_launches++;
+        return MZ_OK;
+    };
+    auto issue = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamWaitEvent(d.stream, jobs[c].up_done, 0));
+        CK(cudaStreamWaitEvent(d.stream, ctx->devs[dev_of(c)].up_t0, 0));  // histogram zeroed
+        CK(cudaEventRecord(d.ev[1], d.stream));
+        int r = launch(c);
+        if (r) return r;
+        CK(cudaEventRecord(d.ev[2], d.stream));
+        return MZ_OK;
+    };
+    std::vector<float> dev_ker(ND, 0.f);
+    auto retire = [&](uint64_t c) -> int {
+        DevState& d = ctx->slot(dev_of(c), slot_of(c));
+        CK(cudaSetDevice(d.device));
+        CK(cudaStreamSynchronize(d.stream));
+        float ker = 0;
+        cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
+        dev_ker[dev_of(c)] += ker;
+        if (d.hs->overflow) {  // capacity estimate too small: redo the chunk with the exact size
+            jobs[c].cap = d.hs->count;
+            int r = launch(c);
+            if (r) return r;
+            CK(cudaStreamSynchronize(d.stream));
+            if (d.hs->overflow) {
+                g_last_error = "internal: exact-capacity re-run overflowed";
+                return MZ_ERR_CUDA;
+            }
+        }
+        return MZ_OK;
+    };
+    const uint64_t R = (kSlots - 1) * ND;
+    for (uint64_t c = 0; c < nchunks + R; c++) {
+        if (c < nchunks && (rc = issue(c))) return rc;
+        if (c >= R && (rc = retire(c - R))) return rc;
+    }
+    // histograms of all devices + seam stitching on the host
+    std::vector<unsigned long long> h(2 * (size_t)nb);
+    for (uint32_t b = 0; b < nb; b++) cnt_out[b] = win_out[b] = 0;
+    for (size_t i = 0; i < ndev; i++) {
+        DevState& d0 = ctx->devs[i];
+        CK(cudaSetDevice(d0.device));
+        CK(cudaMemcpy(h.data(), d0.hist.p, h.size() * 8, cudaMemcpyDeviceToHost));
+        for (uint32_t b = 0; b < nb; b++) cnt_out[b] += h[b], win_out[b] += h[nb + b];
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, d0.up_t0, d0.up_t1) == cudaSuccess) ctx->timing.h2d_ms = std::max(ctx->timing.h2d_ms, ms);
+        ctx->timing.kernel_ms = std::max(ctx->timing.kernel_ms, dev_ker[i]);
+    }
+    // A chunk's last super-k-mer was closed at the chunk's last window; it really ends where the
+    // next chunk's first super-k-mer starts (chunks without any entry lie entirely inside it).
+    uint64_t total = 0;
+    bool have_prev = false;
+    uint32_t prev_bucket = 0;
+    for (uint64_t c = 0; c < nchunks; c++) {
+        const ChunkTail& t = *tail_of(c);
+        const uint64_t lead = (t.count ? t.first_sk : jobs[c].we) - jobs[c].wb;
+        if (have_prev) win_out[prev_bucket] += lead;
+        if (t.count) have_prev = true, prev_bucket = t.last_bucket;
+        total += t.count;
+    }
+    *total_out = total;
+    CK(cudaSetDevice(ctx->devs[0].device));
+    return MZ_OK;
+}
+
 // ASCII -> 2-bit packing, (c >> 1) & 3 per character; one thread per 16 characters.
 __global__ void mz_pack_ascii_kernel(const uint8_t* __restrict__ ascii, uint64_t n,
                                      uint32_t* __restrict__ out, uint64_t nwords) {
@@ -1065,6 +1284,8 @@ void mz_ctx_destroy(mz_ctx* ctx) {
         d.st_in.release(), d.st_pos.release(), d.st_sk.release(), d.st_val.release(), d.st_amb.release(), d.st_offs.release(), d.st_delta.release(), d.delta.release();
         d.amb.release();
         d.in_all.release();
+        d.hist.release();
+        d.st_tail.release();
         for (auto& e : d.up_ev)
             if (e) cudaEventDestroy(e);
         if (d.up_t0) cudaEventDestroy(d.up_t0);
@@ -1138,6 +1359,30 @@ int mz_params_set_tables(mz_params* p, const uint32_t f[4], const uint32_t c[4],
     p->rot = rot;
     p->hash_canonical = hash_canonical ? 1u : 0u;
     return MZ_OK;
+}
+
+int mz_run_bucket_stats(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset, uint64_t n_bp,
+                        uint32_t n_buckets, uint64_t* superkmers_out, uint64_t* windows_out, uint64_t* n_minimizers) {
+    if (!ctx || !p || !superkmers_out || !windows_out || n_buckets == 0) return MZ_ERR_BAD_ARG;
+    if (n_buckets > kBucketMax) return MZ_ERR_UNSUPPORTED;
+    mz_params q = *p;
+    q.want_sk = 1, q.value_bits = 64;
+    if (q.mode != MZ_MODE_MINIMIZER) return MZ_ERR_BAD_ARG;  // super-k-mers exist for minimizers only (src/lib.rs:339)
+    int rc = mz_params_validate(&q, n_bp);
+    if (rc) return rc;
+    for (uint32_t b = 0; b < n_buckets; b++) superkmers_out[b] = windows_out[b] = 0;
+    if (n_minimizers) *n_minimizers = 0;
+    const uint32_t l = q.k + q.w - 1;
+    if (n_bp < l) return MZ_OK;
+    if (!packed) return MZ_ERR_BAD_ARG;
+    ctx->resident = mz_ctx::Resident{};
+    ctx->timing = mz_timing{};
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t total = 0;
+    rc = run_bucket_stats(ctx, q, packed, bp_offset, n_bp, n_buckets, superkmers_out, windows_out, &total);
+    ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    if (n_minimizers) *n_minimizers = total;
+    return rc;
 }
 
 int mz_values(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_offset, uint64_t n_bp,

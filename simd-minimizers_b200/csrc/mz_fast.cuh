@@ -636,6 +636,14 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
             // the iteration after which the lead-in ends (B == 1); B > 1: after block 0 of iteration 0
             const uint32_t lead_b = lead / (uint32_t)SB - (B == 1 ? 1u : 0u);
 
+            // Tiles at the end of a launch (and reads shorter than the longest of their tile): a lane
+            // keeps computing after its last window -- on whatever follows, or on the clamped last word
+            // of the buffer, a homopolymer that emits at every window -- and everything it pushes there
+            // is garbage.  The rows of iterations that lie entirely behind the lane's last window are
+            // dropped at once (the last partly valid iteration is trimmed after the loop), so the garbage
+            // never fills the queue, let alone spills.
+            const bool tile_partial = __any_sync(0xffffffffu, sg.nvalid < a.S);
+            uint32_t qkeep = qa0;
             // a lane close to the end of its rows: the warp moves all its queues to the spill area
             auto spill_check = [&](uint32_t b) {
                 if (__builtin_expect(__any_sync(0xffffffffu, qa > qtrig), 0)) {
@@ -646,6 +654,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                         q_spill<ROWB, XW, QT>(qa0, n, spill + spilled);
                         spilled += n;
                         qa = qa0;
+                        qkeep = qa0;
                         tile_spilled = 1;
                     }
                 }
@@ -872,6 +881,10 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                 }
                 }  // van-Herk blocks of this iteration
                 if (AMB) pclean = (clean >> (SB - 1)) & 1u;
+                if (tile_partial) {
+                    if (eb >= e_hi) qa = qkeep;
+                    else qkeep = qa;
+                }
                 if (!XW) spill_check(b);
             }
             // ---- count: rows pushed, minus those of windows behind the segment's last one ------

@@ -327,6 +327,21 @@ def test_pipelined_host_path_chunk_seams(sm, oracle, monkeypatch):
             _check_case(sm, oracle, packed, 2, n, k, w, c, mode)
 
 
+def test_pipelined_host_path_default_chunks_pageable(sm, oracle, monkeypatch):
+    """The default chunk of the one-device pipeline is 2^25 windows = 8 MiB + 12 bytes of packed
+    input.  Pageable callers go through a bounce buffer filled by a multi-threaded copy whose
+    slices once did not add up to the whole chunk (8 MiB / 16 threads is a multiple of the 4 KiB
+    slice granule, the 12 odd bytes -- the bases of the chunk's last windows -- stayed behind)."""
+    monkeypatch.setenv("MZ_PIPELINE_MIN_WINDOWS", "1")
+    k, w = 31, 19
+    n = (1 << 25) + (1 << 23) + 12345
+    packed = oracle.synth_packed(9, n + 8)  # numpy array: pageable
+    # chunk bytes just above a multiple of (threads x 4 KiB)
+    for chunk_w in (1 << 25, (1 << 24) + 16, 12 * 4096 * 16 * 4 + 8):
+        monkeypatch.setenv("MZ_CHUNK_WINDOWS", str(chunk_w))
+        _check_case(sm, oracle, packed, 0, n, k, w, True, 0)
+
+
 def _oracle_batch(oracle, packed, starts, lens, k, w, canonical, mode, want_sk):
     pr = oracle.make_params(k, w, canonical=canonical, mode=mode)
     offs, pos, sks, vals = [0], [], [], []
