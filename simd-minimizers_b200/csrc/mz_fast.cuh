@@ -122,11 +122,20 @@ inline uint32_t fast_q_trig(uint32_t S, const mz_params& p) {
     return (uint32_t)std::min<double>(S + 1.0, mean + nsig * sigma + 4.0);
 }
 
-// Word `widx` of the packed stream, any index: 0 in front of the buffer, clamped behind it
-// (bases outside the sequence only ever feed windows that are discarded).
+// Word `widx` of the packed stream, any index: 0 in front of the buffer; behind it, words of a
+// fixed pseudo-random sequence (bases outside the sequence only ever feed windows that are
+// discarded, but a repeated word is a 16-periodic sequence whose hashes tie in every window, and
+// the lanes of a launch's last tile that run past the end would take the out-of-line strand rule
+// for every group of windows: measured 190 us per launch).
 __device__ __forceinline__ uint32_t ld_word_any(const uint32_t* seq, uint64_t nwords, int64_t widx) {
     if (widx < 0) return 0u;
-    return __ldg(seq + ((uint64_t)widx < nwords ? (uint64_t)widx : nwords - 1));
+    if ((uint64_t)widx >= nwords) {
+        uint32_t x = (uint32_t)widx * 0x9E3779B1u;
+        x ^= x >> 15;
+        x *= 0x85EBCA77u;
+        return x ^ (x >> 13);
+    }
+    return __ldg(seq + widx);
 }
 
 // Rare path (leftmost != rightmost minimum): strand rule 2*#TG > l on the window's l bases
@@ -884,6 +893,8 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                 if (tile_partial) {
                     if (eb >= e_hi) qa = qkeep;
                     else qkeep = qa;
+                    // every lane is behind its last window: the rest of the tile is idle work
+                    if (__all_sync(0xffffffffu, eb + (uint32_t)SB >= e_hi)) break;
                 }
                 if (!XW) spill_check(b);
             }
