@@ -319,31 +319,45 @@ __device__ __forceinline__ FSeg make_fseg(const KArgs& a, uint32_t tile, uint32_
 
 // ---- ordered emission of one tile (called by a whole warp, once per tile) -------------------------
 // tp[t] = exclusive output offset of lane t inside the tile, tp[32] = the tile's total; entry i of
-// lane t lives at ebase + i * sI + t * sT (shared-memory queue rows, or the global spill area).
-// Lane x & 31 handles output entry x; the owner lane of x is found by walking the lane offsets
-// (x grows by 32 per step and a lane holds ~40 entries, so the walk advances by 0 or 1 almost always).
+// lane t lives in the queue row i of the tile (shared memory).  Lane x & 31 handles output entry x;
+// the owner lane of x is tracked incrementally (x grows by 32 per step and a lane holds ~40 entries,
+// so the owner advances by 0 or 1 almost always).
 
-// 2-bit reverse complement of the low 2*len bits of v (len <= 32), as 32-bit halves
-__device__ __forceinline__ uint64_t revcomp64(uint64_t v, uint32_t len) {
-    uint32_t lo = __brev((uint32_t)(v >> 32)), hi = __brev((uint32_t)v);  // bit reversal swaps the halves
-    // swap the two bits of every base and complement (code ^ 2): m ? (x >> 1) : ~(x << 1), m = 0x5555...
-    lo = ((lo >> 1) & 0x55555555u) | (~(lo << 1) & 0xAAAAAAAAu);
-    hi = ((hi >> 1) & 0x55555555u) | (~(hi << 1) & 0xAAAAAAAAu);
-    return (((uint64_t)hi << 32) | lo) >> (64 - 2 * len);
+// (a & c) | (~b & ~c) in one LOP3
+__device__ __forceinline__ uint32_t lop3_sel_not(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("lop3.b32 %0, %1, %2, %3, 0xB1;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+// swap the two bits of every base and complement it (code ^ 2): bit pairs (hi, lo) -> (~lo, hi)
+__device__ __forceinline__ uint32_t swap_comp32(uint32_t x) { return lop3_sel_not(x >> 1, x << 1, 0x55555555u); }
+// 2-bit reverse complement of the low 2*len bits of (vh:vl) (len <= 32), shifted down; rsh = 64 - 2*len
+__device__ __forceinline__ uint64_t revcomp64(uint32_t vl, uint32_t vh, uint32_t rsh) {
+    const uint32_t lo = swap_comp32(__brev(vh)), hi = swap_comp32(__brev(vl));  // bit reversal swaps the halves
+    return (((uint64_t)hi << 32) | lo) >> rsh;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
 }
 
-template <int VB, bool XW>
-__device__ __forceinline__ void fast_emit_seq(const KArgs& a, uint32_t tile, unsigned long long gbase, uint32_t total,
-                                              const uint32_t* tp, uint32_t qs) {
+// One instance per (value width, entry format), so that the loop carries no run-time switches.
+// FMT 0: minimizer positions; 1: minimizer positions + super-k-mer starts; 2: syncmers (window start, l-mer).
+// The three words of a k-mer (five of an l-mer) are loaded unclamped: tiles so close to the end of
+// the buffer that a load could reach behind it take the out-of-line path (fast_emit_generic).
+template <int VB, bool XW, int FMT, bool CANON>
+__device__ __forceinline__ void fast_emit_tile(const KArgs& a, uint32_t tile, unsigned long long gbase, uint32_t total,
+                                                   uint32_t tp_s, uint32_t qs) {
     // qs = shared address of the tile's queue rows: entry i of lane t at qs + i * ROWB + t * sizeof(QT)
+    // tp_s = shared address of the 33 lane offsets
     using QT = typename std::conditional<XW, uint32_t, uint16_t>::type;
     constexpr uint32_t DBITS = XW ? 8 : 5, DMASK = (1u << DBITS) - 1u, ROWB = 32 * sizeof(QT);
     constexpr int NW = VB == 64 ? 3 : VB == 128 ? 5 : 0;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t Wr = a.w, S = a.S, len = a.val_len;
-    const bool minim = a.mode == MODE_MINIMIZER, want_sk = a.want_sk != 0, canon_val = a.val_canonical != 0;
     uint32_t* const opos = pinned(a.pos + gbase);
-    uint32_t* const osk = pinned(a.sk + (want_sk ? gbase : 0ull));
+    uint32_t* const osk = pinned(a.sk + (FMT == 1 ? gbase : 0ull));
     unsigned long long* const oval = pinned(reinterpret_cast<unsigned long long*>(a.val) + (VB ? gbase * (VB / 64) : 0ull));
     // Tile-uniform addressing.  Lane t's local element 0 is the k-mer at position pos00 + t * S with
     // pos00 = (first window of the tile) - 1 - (lead - w).
@@ -353,43 +367,56 @@ __device__ __forceinline__ void fast_emit_seq(const KArgs& a, uint32_t tile, uns
     const int64_t tbit0 = 2 * ((int64_t)j00 - back) + a.bitbias;
     const uint32_t* const twbase = pinned(a.seq + (tbit0 >> 5));  // never dereferenced below word 0
     const uint32_t tsh = (uint32_t)tbit0 & 31u;
-    const int64_t trem = (int64_t)a.seq_nwords - 1 - (tbit0 >> 5);
-    const uint32_t twlim = trem > 0x7ffffff0ll ? 0x7ffffff0u : (uint32_t)trem;  // last readable word
     const uint32_t mlo = len < 16 ? (1u << (2 * len)) - 1u : 0xffffffffu;
     const uint32_t mhi = len <= 16 ? 0u : len < 32 ? (1u << (2 * len - 32)) - 1u : 0xffffffffu;
+    const uint32_t rsh = 64u - 2u * (len < 32u ? len : 32u);
+    const uint32_t wback = Wr - 1u;
 
     struct Ent {
-        uint32_t rel, sk, w[NW ? NW : 1];
+        uint32_t pos, sk, bp, w[NW ? NW : 1];
     };
-    uint32_t t = 0, lo = 0, hi = tp[1];
-    // locate entry x, decode it, request the words of its k-mer
+    // owner of the entry being located: lane t, tS = t * S, qb = qs + t * sizeof(QT) - tp[t] * ROWB
+    uint32_t t = 0, tS = 0, qb = qs, hi = lds32(tp_s + 4u);
+    const uint32_t last = total - 1u;
+    // locate entry x (< total), decode it, request the words of its k-mer
     auto stageB = [&](uint32_t x, Ent& e) {
-        while (x >= hi) {  // 0 or 1 steps almost always (a lane holds more than 32 entries on average)
-            t++;
-            lo = hi;
-            hi = tp[t + 1];
+        if (x >= hi) {
+            uint32_t lo;
+            do {
+                t++;
+                lo = hi;
+                hi = lds32(tp_s + 4u * t + 4u);
+            } while (x >= hi);
+            qb = qs + t * (uint32_t)sizeof(QT) - lo * ROWB;
+            tS = t * S;
         }
-        const uint32_t v = q_load<XW>(qs + (x - lo) * ROWB + t * (uint32_t)sizeof(QT));
-        const uint32_t posl = v >> DBITS, wst = posl + (v & DMASK) - (Wr - 1u);  // selected k-mer, first k-mer of the window
-        const uint32_t base = t * S;
-        e.rel = base + (minim ? posl : wst);  // reported k-mer, counted from the tile's element 0
-        e.sk = pos00 + base + wst;            // = index of the window
+        const uint32_t v = q_load<XW>(qb + x * ROWB);
+        const uint32_t posl = v >> DBITS;  // selected k-mer
+        uint32_t rel = tS + posl;          // reported k-mer, counted from the tile's element 0
+        if (FMT != 0) {
+            const uint32_t wst = rel + (v & DMASK) - wback;  // first k-mer of the window
+            e.sk = pos00 + wst;                               // = index of the window
+            if (FMT == 2) rel = wst;
+        }
+        e.pos = pos00 + rel;
+        e.bp = tsh + 2u * rel;
         if (NW) {
-            const uint32_t wl = (tsh + 2u * e.rel) >> 5;
+            const uint32_t* const wp = twbase + (e.bp >> 5);
 #pragma unroll
-            for (int q = 0; q < NW; q++) e.w[q] = __ldg(twbase + min(wl + q, twlim));
+            for (int q = 0; q < NW; q++) e.w[q] = __ldg(wp + q);
         }
     };
-    auto stageC = [&](uint32_t x, const Ent& e) {
-        __stcs(opos + x, pos00 + e.rel);  // streaming stores: the outputs are not read again here
-        if (want_sk) __stcs(osk + x, e.sk);
-        const uint32_t sh = (tsh + 2u * e.rel) & 31u;
+    auto stageC = [&](uint32_t x, const Ent& e, auto tail) {
+        if (decltype(tail)::value && x >= total) return;  // the last batch of 32 may be partial
+        __stcs(opos + x, e.pos);          // streaming stores: the outputs are not read again here
+        if (FMT == 1) __stcs(osk + x, e.sk);
+        const uint32_t sh = e.bp & 31u;
         if (VB == 64) {
             const uint32_t vl = __funnelshift_r(e.w[0], e.w[NW > 1 ? 1 : 0], sh) & mlo;
             const uint32_t vh = __funnelshift_r(e.w[NW > 1 ? 1 : 0], e.w[NW > 2 ? 2 : 0], sh) & mhi;
             uint64_t v = ((uint64_t)vh << 32) | vl;
-            if (canon_val) {
-                const uint64_t r = revcomp64(v, len);
+            if (CANON) {
+                const uint64_t r = revcomp64(vl, vh, rsh);
                 v = r < v ? r : v;
             }
             __stcs(oval + x, (unsigned long long)v);
@@ -404,10 +431,10 @@ __device__ __forceinline__ void fast_emit_seq(const KArgs& a, uint32_t tile, uns
                 vhi &= (1ull << (2 * (len - 32))) - 1ull;
             }
             uint64_t olo = vlo, ohi = vhi;
-            if (canon_val) {
+            if (CANON) {
                 // reverse the 128-bit value 2 bits at a time, complement, shift down by 128 - 2*len
-                const uint64_t rhi = swap_pairs64(__brevll(vlo)) ^ 0xAAAAAAAAAAAAAAAAull;
-                const uint64_t rlo = swap_pairs64(__brevll(vhi)) ^ 0xAAAAAAAAAAAAAAAAull;
+                const uint64_t rhi = ((uint64_t)swap_comp32(__brev((uint32_t)vlo)) << 32) | swap_comp32(__brev((uint32_t)(vlo >> 32)));
+                const uint64_t rlo = ((uint64_t)swap_comp32(__brev((uint32_t)vhi)) << 32) | swap_comp32(__brev((uint32_t)(vhi >> 32)));
                 const uint32_t s = 128 - 2 * len;  // 0..126, even
                 uint64_t qlo, qhi;
                 if (s == 0) qlo = rlo, qhi = rhi;
@@ -419,20 +446,56 @@ __device__ __forceinline__ void fast_emit_seq(const KArgs& a, uint32_t tile, uns
             asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(oval + 2ull * x), "l"(olo), "l"(ohi) : "memory");
         }
     };
-    // software pipeline, unrolled twice (two register sets instead of copies): entry x + 32 is
-    // located and its words are requested while entry x is turned into a value and stored
+    // software pipeline over batches of 32 entries, unrolled twice (two register sets instead of
+    // copies): entry x + 32 is located and its words are requested while entry x is turned into a
+    // value and stored.  The batch loop is warp-uniform: lanes behind the last entry re-do the last one.
+    const uint32_t nbatch = (total + 31u) >> 5;
+    const std::integral_constant<bool, false> full;
+    const std::integral_constant<bool, true> tail;
     Ent e0, e1;
-    uint32_t x = lane;
-    if (x < total) stageB(x, e0);
+    uint32_t x = lane, i = 1;
+    stageB(min(x, last), e0);
 #pragma unroll 1
-    while (x < total) {
-        if (x + 32 < total) stageB(x + 32, e1);
-        stageC(x, e0);
-        x += 32;
-        if (x >= total) break;
-        if (x + 32 < total) stageB(x + 32, e0);
-        stageC(x, e1);
-        x += 32;
+    for (;;) {
+        if (i >= nbatch) {
+            stageC(x, e0, tail);
+            break;
+        }
+        stageB(min(x + 32u, last), e1);
+        stageC(x, e0, full);
+        i++;
+        if (i >= nbatch) {
+            stageC(x + 32u, e1, tail);
+            break;
+        }
+        stageB(min(x + 64u, last), e0);
+        stageC(x + 32u, e1, full);
+        i++;
+        x += 64u;
+    }
+}
+
+// May a k-mer word load of this tile reach behind the buffer?  (conservative bound on the tile's
+// last element: 32 lanes x S windows + lead-in + one loop iteration; 5 words per l-mer)
+__device__ __forceinline__ bool fast_tile_at_buffer_end(const KArgs& a, uint32_t tile) {
+    const uint64_t j00 = a.wbeg + (uint64_t)tile * 32u * a.S;
+    const int64_t tbit0 = 2 * ((int64_t)j00 - 1 - (int64_t)(a.lead - a.w)) + a.bitbias;
+    const int64_t wmax = (tbit0 >> 5) + ((31u + 2u * (32u * a.S + a.lead + 64u)) >> 5) + 5;
+    return wmax >= (int64_t)a.seq_nwords;
+}
+// Run-time selection of the emission instance (warp-uniform, once per tile).
+template <bool XW, bool SYNC, bool CANON>
+__device__ __forceinline__ void fast_emit_seq(const KArgs& a, uint32_t tile, unsigned long long gbase, uint32_t total,
+                                              uint32_t tp_s, uint32_t qs) {
+    constexpr int F0 = SYNC ? 2 : 0, F1 = SYNC ? 2 : 1;
+    if (SYNC || !a.want_sk) {
+        if (a.value_bits == 64) fast_emit_tile<64, XW, F0, CANON>(a, tile, gbase, total, tp_s, qs);
+        else if (a.value_bits == 128) fast_emit_tile<128, XW, F0, CANON>(a, tile, gbase, total, tp_s, qs);
+        else fast_emit_tile<0, XW, F0, false>(a, tile, gbase, total, tp_s, qs);
+    } else {
+        if (a.value_bits == 64) fast_emit_tile<64, XW, F1, CANON>(a, tile, gbase, total, tp_s, qs);
+        else if (a.value_bits == 128) fast_emit_tile<128, XW, F1, CANON>(a, tile, gbase, total, tp_s, qs);
+        else fast_emit_tile<0, XW, F1, false>(a, tile, gbase, total, tp_s, qs);
     }
 }
 
@@ -958,11 +1021,9 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                 ebase = q0 + (size_t)pb * QROWS * ROWB;
                 sI = (uint32_t)ROWB, sT = (uint32_t)sizeof(QT);
             }
-            if (a.n_reads == 0 && !p_spilled) {
+            if (a.n_reads == 0 && !p_spilled && !(a.value_bits != 0 && fast_tile_at_buffer_end(a, tile_e))) {
                 const uint32_t qs = q0s - lane * (uint32_t)sizeof(QT) + pb * QROWS * (uint32_t)ROWB;
-                if (a.value_bits == 64) fast_emit_seq<64, XW>(a, tile_e, gbase, total, tpe, qs);
-                else if (a.value_bits == 128) fast_emit_seq<128, XW>(a, tile_e, gbase, total, tpe, qs);
-                else fast_emit_seq<0, XW>(a, tile_e, gbase, total, tpe, qs);
+                fast_emit_seq<XW, SYNC, LR>(a, tile_e, gbase, total, (uint32_t)__cvta_generic_to_shared(tpe), qs);
             } else {
                 if (a.value_bits == 64) fast_emit_generic<64, XW>(a, tile_e, gbase, total, tpe, ebase, sI, sT);
                 else if (a.value_bits == 128) fast_emit_generic<128, XW>(a, tile_e, gbase, total, tpe, ebase, sI, sT);
