@@ -142,6 +142,11 @@ int mz_run(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_t bp_o
  * `d_packed` must hold the whole sequence [bp_offset, bp_offset+n_bp).  out->count is written
  * on the host after the stream is synchronised.  Used for device-resident timing and by
  * callers that keep consuming on the GPU.
+ * Device-buffer requirements (checked where possible, MZ_ERR_BAD_ARG otherwise): pos / sk 4-byte
+ * aligned, val 8-byte aligned (16-byte for value_bits == 128: (lo, hi) is one 16-byte store);
+ * d_packed (and d_ambiguous) may start at any byte, but are read as aligned 32-bit words, so the
+ * bytes up to the next 4-byte boundary behind the last base must be readable (any cudaMalloc'ed
+ * buffer is; a sub-allocation that ends exactly at the end of its arena needs 3 bytes of padding).
  */
 int mz_run_device(mz_ctx* ctx, int dev_index, const mz_params* p, const void* d_packed,
                   uint64_t bp_offset, uint64_t n_bp, uint64_t win_begin, uint64_t win_end,

@@ -100,6 +100,13 @@ public:
         for (size_t i = 0; i < v.size(); i++) v[i] = {(*pos_)[i], vals[i]};
         return v;
     }
+    // (pos, (lo, hi)) -- src/lib.rs:622-629
+    std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> pos_and_values_u128() const {
+        const auto vals = values_u128();
+        std::vector<std::pair<uint32_t, std::pair<uint64_t, uint64_t>>> v(vals.size());
+        for (size_t i = 0; i < v.size(); i++) v[i] = {(*pos_)[i], vals[i]};
+        return v;
+    }
     const std::vector<uint32_t>& positions() const { return *pos_; }
 
 private:

@@ -65,6 +65,25 @@ pub struct mz_ctx {
     _private: [u8; 0],
 }
 
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct mz_pcie_result {
+    pub h2d_gbs: f64,
+    pub d2h_gbs: f64,
+    pub bidir_h2d_gbs: f64,
+    pub bidir_d2h_gbs: f64,
+    pub n_devices: u32,
+    pub reserved: u32,
+}
+
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct mz_alu_result {
+    pub lane_ops_per_s: f64,
+    pub ms: f32,
+    pub sm_count: u32,
+}
+
 extern "C" {
     pub fn mz_abi_version() -> u32;
     pub fn mz_strerror(code: c_int) -> *const c_char;
@@ -74,6 +93,8 @@ extern "C" {
     pub fn mz_params_mulhash(p: *mut mz_params, k: u32, w: u32, mode: u32, canonical: u32) -> c_int;
     pub fn mz_params_set_nthash(p: *mut mz_params, hash_canonical: u32) -> c_int;
     pub fn mz_params_set_mulhash(p: *mut mz_params, hash_canonical: u32) -> c_int;
+    pub fn mz_params_set_tables(p: *mut mz_params, f: *const u32, c: *const u32, rot: u32,
+                                hash_canonical: u32) -> c_int;
     pub fn mz_params_validate(p: *const mz_params, n_bp: u64) -> c_int;
     pub fn mz_ctx_create(device_ids: *const c_int, n_devices: c_int, ctx: *mut *mut mz_ctx) -> c_int;
     pub fn mz_ctx_destroy(ctx: *mut mz_ctx);
@@ -104,4 +125,11 @@ extern "C" {
                            ambiguous_out: *mut u8) -> c_int;
     pub fn mz_run_ascii_skip_ambiguous(ctx: *mut mz_ctx, p: *const mz_params, ascii: *const c_char,
                                        n: u64, out: *mut mz_out) -> c_int;
+    pub fn mz_values(ctx: *mut mz_ctx, p: *const mz_params, packed: *const u8, bp_offset: u64, n_bp: u64,
+                     pos: *const u32, n_pos: u64, value_bits: u32, val_out: *mut u64) -> c_int;
+    pub fn mz_run_bucket_stats(ctx: *mut mz_ctx, p: *const mz_params, packed: *const u8, bp_offset: u64,
+                               n_bp: u64, n_buckets: u32, superkmers_out: *mut u64, windows_out: *mut u64,
+                               n_minimizers: *mut u64) -> c_int;
+    pub fn mz_pcie_probe(ctx: *mut mz_ctx, bytes_per_device: u64, reps: u32, res: *mut mz_pcie_result) -> c_int;
+    pub fn mz_alu_probe(ctx: *mut mz_ctx, dev_index: c_int, res: *mut mz_alu_result) -> c_int;
 }

@@ -1530,6 +1530,11 @@ static int run_device_impl(mz_ctx* ctx, int dev_index, const mz_params* p, const
     if (win_end == 0 || win_end > nwin) win_end = nwin;
     if (win_begin >= win_end) return MZ_OK;
     if (!d_packed || !out->pos || (p->want_sk && !out->sk) || (p->value_bits && !out->val)) return MZ_ERR_BAD_ARG;
+    // the kernels store whole elements: u32 positions, u64 values, (lo, hi) pairs as one 16-byte store
+    auto misaligned = [](const void* q, uintptr_t al) { return (reinterpret_cast<uintptr_t>(q) & (al - 1)) != 0; };
+    if (misaligned(out->pos, 4) || (p->want_sk && misaligned(out->sk, 4)) ||
+        (p->value_bits && misaligned(out->val, p->value_bits == 128 ? 16 : 8)))
+        return MZ_ERR_BAD_ARG;
 
     DevState& d = ctx->devs[dev_index];
     CK(cudaSetDevice(d.device));

@@ -210,48 +210,38 @@ __device__ __forceinline__ void q_push_ne(uint32_t& qa, uint32_t a, uint32_t b, 
                      "@p st.shared.u16 [%0], lo;\n\t@p add.u32 %0, %0, %4;\n\t}"
                      : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "n"(ROWB));
 }
-// the same with the pointer bump as rowb * one + qa (FMA pipe; rowb holds ROWB, one holds 1)
-template <bool WIDE>
-__device__ __forceinline__ void q_push_ne_fma(uint32_t& qa, uint32_t a, uint32_t b, uint32_t ent, uint32_t rowb, uint32_t one) {
-    if constexpr (WIDE)
-        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.u32 p, %1, %2;\n\t@p st.shared.u32 [%0], %3;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t}"
-                     : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "r"(rowb), "r"(one));
-    else
-        asm volatile("{\n\t.reg .pred p;\n\t.reg .b16 lo;\n\tsetp.ne.u32 p, %1, %2;\n\tcvt.u16.u32 lo, %3;\n\t"
-                     "@p st.shared.u16 [%0], lo;\n\t@p mad.lo.u32 %0, %4, %5, %0;\n\t}"
-                     : "+r"(qa) : "r"(a), "r"(b), "r"(ent), "r"(rowb), "r"(one));
-}
 // Up to four consecutive windows in one go (NG of them): entry u is pushed when its selection r[u]
 // differs from the one before it (prev, r[0], r[1], r[2]).  One asm block, so that the queue
 // pointer stays in one register across the four predicated bumps.
+// (bump = one * ROWB + qa with ROWB as an immediate: only `one` needs a register)
 template <bool WIDE, int NG>
 __device__ __forceinline__ void q_push4_ne_fma(uint32_t& qa, uint32_t prev, const uint32_t (&r)[4], const uint32_t (&e)[4],
-                                               uint32_t rowb, uint32_t one) {
+                                               uint32_t one) {
     if constexpr (WIDE) {
         asm volatile(
             "{\n\t.reg .pred p0, p1, p2, p3;\n\t"
             "setp.ne.u32 p0, %1, %9;\n\tsetp.ne.u32 p1, %2, %1;\n\tsetp.ne.u32 p2, %3, %2;\n\tsetp.ne.u32 p3, %4, %3;\n\t"
-            "@p0 st.shared.u32 [%0], %5;\n\t@p0 mad.lo.u32 %0, %10, %11, %0;\n\t"
-            "@p1 st.shared.u32 [%0], %6;\n\t@p1 mad.lo.u32 %0, %10, %11, %0;\n\t"
-            "@p2 st.shared.u32 [%0], %7;\n\t@p2 mad.lo.u32 %0, %10, %11, %0;\n\t"
-            "@p3 st.shared.u32 [%0], %8;\n\t@p3 mad.lo.u32 %0, %10, %11, %0;\n\t}"
+            "@p0 st.shared.u32 [%0], %5;\n\t@p0 mad.lo.u32 %0, %10, 128, %0;\n\t"
+            "@p1 st.shared.u32 [%0], %6;\n\t@p1 mad.lo.u32 %0, %10, 128, %0;\n\t"
+            "@p2 st.shared.u32 [%0], %7;\n\t@p2 mad.lo.u32 %0, %10, 128, %0;\n\t"
+            "@p3 st.shared.u32 [%0], %8;\n\t@p3 mad.lo.u32 %0, %10, 128, %0;\n\t}"
             : "+r"(qa)
             : "r"(r[0]), "r"(NG > 1 ? r[1] : r[0]), "r"(NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0])),
               "r"(NG > 3 ? r[3] : (NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0]))), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]),
-              "r"(prev), "r"(rowb), "r"(one));
+              "r"(prev), "r"(one));
     } else {
         asm volatile(
             "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b16 l0, l1, l2, l3;\n\t"
             "setp.ne.u32 p0, %1, %9;\n\tsetp.ne.u32 p1, %2, %1;\n\tsetp.ne.u32 p2, %3, %2;\n\tsetp.ne.u32 p3, %4, %3;\n\t"
             "cvt.u16.u32 l0, %5;\n\tcvt.u16.u32 l1, %6;\n\tcvt.u16.u32 l2, %7;\n\tcvt.u16.u32 l3, %8;\n\t"
-            "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %10, %11, %0;\n\t"
-            "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %10, %11, %0;\n\t"
-            "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %10, %11, %0;\n\t"
-            "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %10, %11, %0;\n\t}"
+            "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %10, 64, %0;\n\t"
+            "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %10, 64, %0;\n\t"
+            "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %10, 64, %0;\n\t"
+            "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %10, 64, %0;\n\t}"
             : "+r"(qa)
             : "r"(r[0]), "r"(NG > 1 ? r[1] : r[0]), "r"(NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0])),
               "r"(NG > 3 ? r[3] : (NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0]))), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]),
-              "r"(prev), "r"(rowb), "r"(one));
+              "r"(prev), "r"(one));
     }
 }
 
@@ -618,7 +608,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
     // opaque 1 for imad(): a kernel argument, so that ptxas cannot fold x * 1 + c back into an
     // ALU-pipe add (the positions and the queue pointer are bumped on the idle FMA pipe)
     const uint32_t one = a.one;
-    const uint32_t rowb = one * (uint32_t)ROWB;
+    static_assert(ROWB == (XW ? 128 : 64), "q_push4_ne_fma hard-codes the row size");
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
     const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (Wr - 1) / 2, so2 = a.mode == MODE_CLOSED ? Wr - 1 : (Wr - 1) / 2;
 
@@ -649,14 +639,15 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
             // bW-1 (base -1 = virtual 'A').  Both are addressed with one extra virtual word in
             // front (+32 bits) so that the bit position never goes negative.
             const int64_t w0abs = sg.bit0 >> 5;
-            const uint32_t* const wbase = a.seq + w0abs;   // only dereferenced inside the buffer
+            // (kept in registers: ptxas otherwise re-derives it from a.seq in front of every prefetch)
+            const uint32_t* const wbase = pinned(a.seq + w0abs);   // only dereferenced inside the buffer
             const uint32_t sh0 = (uint32_t)sg.bit0 & 31u;
             // may any (pre)fetch of this thread touch a word outside the buffer?
             const uint32_t wmax = ((sh0 + 32u + 2u * (k - 1) + 2u * (NB + 1) * SB) >> 5) + 3u;
             const bool clampd = w0abs < 1 || (uint64_t)w0abs + wmax >= a.seq_nwords;
             auto ldw = [&](uint32_t wl1) -> uint32_t {  // wl1 = word offset + 1 (virtual word 0)
                 if (wl1 == 0) return 0u;
-                if (clampd) return ld_word_any(a.seq, a.seq_nwords, w0abs + (int64_t)wl1 - 1);
+                if (clampd) return ld_word_any(a.seq, a.seq_nwords, (sg.bit0 >> 5) + (int64_t)wl1 - 1);
                 return __ldg(wbase + (wl1 - 1));
             };
             // ---- prologue: consume k-1 bases, two per table step (leaving bases = virtual 'A') --
@@ -904,10 +895,10 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
 #pragma unroll
                             for (int u = 0; u < 4; u++)
                                 ge[u] = u < ng ? (XW ? imad(gr[u] & 0xffffu, DMUL, gp[u]) : imad(gr[u], DMUL, gp[u])) : 0u;
-                            if (ng == 4) q_push4_ne_fma<XW, 4>(qa, prev, gr, ge, rowb, one);
-                            else if (ng == 3) q_push4_ne_fma<XW, 3>(qa, prev, gr, ge, rowb, one);
-                            else if (ng == 2) q_push4_ne_fma<XW, 2>(qa, prev, gr, ge, rowb, one);
-                            else q_push4_ne_fma<XW, 1>(qa, prev, gr, ge, rowb, one);
+                            if (ng == 4) q_push4_ne_fma<XW, 4>(qa, prev, gr, ge, one);
+                            else if (ng == 3) q_push4_ne_fma<XW, 3>(qa, prev, gr, ge, one);
+                            else if (ng == 2) q_push4_ne_fma<XW, 2>(qa, prev, gr, ge, one);
+                            else q_push4_ne_fma<XW, 1>(qa, prev, gr, ge, one);
                             prev = gr[ng - 1];
                         } else {
 #pragma unroll

@@ -26,6 +26,20 @@ def test_header_symbols_exported(ffi):
     assert L.mz_abi_version() == 1
 
 
+def test_rust_sys_bindings_cover_the_header():
+    """rust/mzb200-sys declares exactly the header's entry points (the crate cannot be compiled in
+    this image, so at least the symbol lists must not drift apart)."""
+    hdr = open(os.path.join(ROOT, "include", "mz_b200.h")).read()
+    declared = set(re.findall(r"\b(mz_[a-z0-9_]+)\s*\(", hdr))
+    rs = open(os.path.join(ROOT, "rust", "mzb200-sys", "src", "lib.rs")).read()
+    bound = set(re.findall(r"pub fn (mz_[a-z0-9_]+)\s*\(", rs))
+    assert declared == bound, declared ^ bound
+    # the safe shim only calls what the -sys crate binds
+    shim = open(os.path.join(ROOT, "rust", "simd-minimizers-b200", "src", "lib.rs")).read()
+    used = set(re.findall(r"sys::(mz_[a-z0-9_]+)\s*\(", shim))
+    assert used <= bound, used - bound
+
+
 def test_struct_layout_matches_header(ffi):
     assert C.sizeof(ffi.MzParams) == 4 * (6 + 4 + 4 + 2 + 2)
     assert C.sizeof(ffi.MzOut) == 40
