@@ -110,7 +110,9 @@ inline double fast_density(const mz_params& p) {
 inline uint32_t fast_q_bufs(const mz_params& p) {
     static const int force = getenv("MZ_FAST_NBUF") ? atoi(getenv("MZ_FAST_NBUF")) : 0;
     if (force == 1 || force == 2) return (uint32_t)force;
-    return fast_density(p) >= 0.175 ? 1u : 2u;
+    // (syncmers push no lead-in entries that are dropped again and their emission is the longer one
+    // with l-mer values: closed syncmers w = 11, density 0.18, measured 422 -> 434 Gbp/s with two buffers)
+    return fast_density(p) >= (p.mode == MZ_MODE_MINIMIZER ? 0.175 : 0.19) ? 1u : 2u;
 }
 // rows a lane may hold before the warp spills: expected entries of a segment + 6 sigma-ish slack
 inline uint32_t fast_q_trig(uint32_t S, const mz_params& p) {
@@ -245,6 +247,26 @@ __device__ __forceinline__ void q_push4_ne_fma(uint32_t& qa, uint32_t prev, cons
     }
 }
 
+// Syncmers, windows <= 32: the low five bits of an entry are the distance d of the selected k-mer
+// from the window end, and the window is a syncmer when bit d of `smask` is set (closed: d in
+// {0, W-1}; open: d = (W-1)/2; src/syncmers.rs:33-37).  SHF.R.W takes the shift amount mod 32, so
+// the test is one shift and one LOP3 with a predicate result per window.  m[u] = smask for the
+// group's windows, 0 for the slots behind the last one.
+__device__ __forceinline__ void q_push4_mask_fma(uint32_t& qa, const uint32_t (&m)[4], const uint32_t (&e)[4], uint32_t one) {
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b16 l0, l1, l2, l3;\n\t.reg .b32 t0, t1, t2, t3;\n\t"
+        "shf.r.wrap.b32 t0, %1, 0, %5;\n\tshf.r.wrap.b32 t1, %2, 0, %6;\n\tshf.r.wrap.b32 t2, %3, 0, %7;\n\tshf.r.wrap.b32 t3, %4, 0, %8;\n\t"
+        "and.b32 t0, t0, 1;\n\tand.b32 t1, t1, 1;\n\tand.b32 t2, t2, 1;\n\tand.b32 t3, t3, 1;\n\t"
+        "setp.ne.u32 p0, t0, 0;\n\tsetp.ne.u32 p1, t1, 0;\n\tsetp.ne.u32 p2, t2, 0;\n\tsetp.ne.u32 p3, t3, 0;\n\t"
+        "cvt.u16.u32 l0, %5;\n\tcvt.u16.u32 l1, %6;\n\tcvt.u16.u32 l2, %7;\n\tcvt.u16.u32 l3, %8;\n\t"
+        "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %9, 64, %0;\n\t"
+        "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %9, 64, %0;\n\t"
+        "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %9, 64, %0;\n\t"
+        "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %9, 64, %0;\n\t}"
+        : "+r"(qa)
+        : "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(one));
+}
+
 // entry at shared address `addr`
 template <bool WIDE>
 __device__ __forceinline__ uint32_t q_load(uint32_t addr) {
@@ -361,6 +383,14 @@ __device__ __forceinline__ void fast_emit_tile(const KArgs& a, uint32_t tile, un
     const uint32_t mhi = len <= 16 ? 0u : len < 32 ? (1u << (2 * len - 32)) - 1u : 0xffffffffu;
     const uint32_t rsh = 64u - 2u * (len < 32u ? len : 32u);
     const uint32_t wback = Wr - 1u;
+    // 128-bit values: word masks of the 2*len valid bits, and the shift 128 - 2*len of the reverse complement
+    uint32_t vm[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+        const int nb = (int)(2u * len) - 32 * q;  // valid bits in word q
+        vm[q] = nb <= 0 ? 0u : nb >= 32 ? 0xffffffffu : (1u << nb) - 1u;
+    }
+    const uint32_t rs128 = 128u - 2u * (len < 64u ? len : 64u), rsw = rs128 >> 5, rsb = rs128 & 31u;
 
     struct Ent {
         uint32_t pos, sk, bp, w[NW ? NW : 1];
@@ -411,29 +441,32 @@ __device__ __forceinline__ void fast_emit_tile(const KArgs& a, uint32_t tile, un
             }
             __stcs(oval + x, (unsigned long long)v);
         } else if (VB == 128) {
-            uint64_t vlo = (uint64_t)__funnelshift_r(e.w[0], e.w[NW > 1 ? 1 : 0], sh) | ((uint64_t)__funnelshift_r(e.w[NW > 1 ? 1 : 0], e.w[NW > 2 ? 2 : 0], sh) << 32);
-            uint64_t vhi = (uint64_t)__funnelshift_r(e.w[NW > 2 ? 2 : 0], e.w[NW > 3 ? 3 : 0], sh) |
-                           ((uint64_t)__funnelshift_r(e.w[NW > 3 ? 3 : 0], e.w[NW > 4 ? 4 : 0], sh) << 32);
-            if (len <= 32) {
-                vhi = 0;
-                if (len < 32) vlo &= (1ull << (2 * len)) - 1ull;
-            } else if (len < 64) {
-                vhi &= (1ull << (2 * (len - 32))) - 1ull;
-            }
-            uint64_t olo = vlo, ohi = vhi;
+            // the l-mer as four 32-bit words (low to high), masked to 2*len bits
+            uint32_t v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) v[q] = __funnelshift_r(e.w[NW > q ? q : 0], e.w[NW > q + 1 ? q + 1 : 0], sh) & vm[q];
+            uint32_t o0 = v[0], o1 = v[1], o2 = v[2], o3 = v[3];
             if (CANON) {
-                // reverse the 128-bit value 2 bits at a time, complement, shift down by 128 - 2*len
-                const uint64_t rhi = ((uint64_t)swap_comp32(__brev((uint32_t)vlo)) << 32) | swap_comp32(__brev((uint32_t)(vlo >> 32)));
-                const uint64_t rlo = ((uint64_t)swap_comp32(__brev((uint32_t)vhi)) << 32) | swap_comp32(__brev((uint32_t)(vhi >> 32)));
-                const uint32_t s = 128 - 2 * len;  // 0..126, even
-                uint64_t qlo, qhi;
-                if (s == 0) qlo = rlo, qhi = rhi;
-                else if (s < 64) qlo = (rlo >> s) | (rhi << (64 - s)), qhi = rhi >> s;
-                else qlo = rhi >> (s - 64), qhi = 0;
-                if (qhi < vhi || (qhi == vhi && qlo < vlo)) olo = qlo, ohi = qhi;
+                // reverse the 128 bits two at a time and complement (word q of the result comes from
+                // word 3 - q), then shift down by s = 128 - 2*len = 32 * rsw + rsb (tile-uniform)
+                const uint32_t r0 = swap_comp32(__brev(v[3])), r1 = swap_comp32(__brev(v[2]));
+                const uint32_t r2 = swap_comp32(__brev(v[1])), r3 = swap_comp32(__brev(v[0]));
+                uint32_t q0, q1, q2, q3;
+                if (rsw == 0) {
+                    q0 = __funnelshift_r(r0, r1, rsb), q1 = __funnelshift_r(r1, r2, rsb), q2 = __funnelshift_r(r2, r3, rsb), q3 = r3 >> rsb;
+                } else if (rsw == 1) {
+                    q0 = __funnelshift_r(r1, r2, rsb), q1 = __funnelshift_r(r2, r3, rsb), q2 = r3 >> rsb, q3 = 0u;
+                } else if (rsw == 2) {
+                    q0 = __funnelshift_r(r2, r3, rsb), q1 = r3 >> rsb, q2 = 0u, q3 = 0u;
+                } else {
+                    q0 = r3 >> rsb, q1 = 0u, q2 = 0u, q3 = 0u;
+                }
+                const uint64_t qh = ((uint64_t)q3 << 32) | q2, vh = ((uint64_t)v[3] << 32) | v[2];
+                const uint64_t ql = ((uint64_t)q1 << 32) | q0, vl = ((uint64_t)v[1] << 32) | v[0];
+                if (qh < vh || (qh == vh && ql < vl)) o0 = q0, o1 = q1, o2 = q2, o3 = q3;
             }
             // 16-byte streaming store (consecutive lanes -> 512 contiguous bytes per warp)
-            asm volatile("st.global.cs.v2.u64 [%0], {%1, %2};" ::"l"(oval + 2ull * x), "l"(olo), "l"(ohi) : "memory");
+            asm volatile("st.global.cs.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(oval + 2ull * x), "r"(o0), "r"(o1), "r"(o2), "r"(o3) : "memory");
         }
     };
     // software pipeline over batches of 32 entries, unrolled twice (two register sets instead of
@@ -611,6 +644,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
     static_assert(ROWB == (XW ? 128 : 64), "q_push4_ne_fma hard-codes the row size");
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
     const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (Wr - 1) / 2, so2 = a.mode == MODE_CLOSED ? Wr - 1 : (Wr - 1) / 2;
+    const uint32_t smask = (1u << (so1 & 31u)) | (1u << (so2 & 31u));  // !XW: bit d set <=> syncmer
 
     __syncthreads();  // table + misc ready; from here on every warp works on its own
 
@@ -900,6 +934,14 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                             else if (ng == 2) q_push4_ne_fma<XW, 2>(qa, prev, gr, ge, one);
                             else q_push4_ne_fma<XW, 1>(qa, prev, gr, ge, one);
                             prev = gr[ng - 1];
+                        } else if (SYNC && !AMB && !XW) {
+                            uint32_t ge[4], gk[4];
+#pragma unroll
+                            for (int u = 0; u < 4; u++) {
+                                ge[u] = u < ng ? imad(gr[u], DMUL, gp[u]) : 0u;
+                                gk[u] = u < ng ? smask : 0u;
+                            }
+                            q_push4_mask_fma(qa, gk, ge, one);
                         } else {
 #pragma unroll
                             for (int u = 0; u < 4; u++) {
