@@ -751,8 +751,9 @@ def bench_reads(env, cfg):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
             "config": workload_config("c5", cfg, 0, {"checksum_first_%d_entries" % CHECK_PREFIX: checksum_entries(h_pos.np[:CHECK_PREFIX], None)}),
             "result": {"reads": n_reads, "outputs": cnt, "checksum": checksum_entries(h_pos.np[:cnt], None),
-                       "value_is": "reads x 150 bp / (busiest device's summed kernel time per step, CUDA events): the "
-                                   "chunks' launches run while other chunks' copies are in flight"},
+                       "value_is": "all reads x 150 bp / (busiest device's kernel time per step: CUDA events around "
+                                   "every chunk launch, minus the time a launch spent queued behind the device's "
+                                   "previous chunk); the launches run while other chunks' copies are in flight"},
             "roofline": {"bound": "hbm", "achieved": alg_bytes / (ker_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
                          "frac": alg_bytes / (ker_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": alg_bytes,

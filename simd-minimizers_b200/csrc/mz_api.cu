@@ -137,7 +137,8 @@ struct DevState {
     int sm_count = 148;
     size_t smem_optin = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // H2D begin/end, kernel end, D2H end, D2H begin
+    // H2D begin/end, kernel end, D2H end, D2H begin, kernel end kept until the slot's next chunk
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<unsigned long long> scratch;  // [0]=count [1]=ticket|overflow [2..]=tile_state
     DevBuf<uint32_t> rows;               // fast kernel per-block record rows
     DevBuf<uint8_t> in;
@@ -352,6 +353,25 @@ int enqueue_run(DevState& d, const mz_params& p, mz::KArgs a, uint64_t wbeg, uin
     return MZ_OK;
 }
 
+// Kernel time of a chunk in a pipeline: ev[1] .. ev[2] of its slot, minus the time its launch spent
+// queued behind the previous chunk of the same device (another stream; every launch occupies all
+// SMs, so the launches of one device run one after the other): the device was busy with THIS chunk
+// from max(ev[1], kernel end of the previous chunk) on.  prev = slot of the device's previous chunk
+// (its ev[5] has completed), or nullptr.
+float chunk_kernel_ms(DevState& d, DevState* prev) {
+    float ker = 0, since_prev = 0;
+    if (cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]) != cudaSuccess) {
+        cudaGetLastError();
+        return 0.f;
+    }
+    if (prev && cudaEventElapsedTime(&since_prev, prev->ev[5], d.ev[2]) == cudaSuccess) {
+        if (since_prev >= 0.f && since_prev < ker) ker = since_prev;
+    } else {
+        cudaGetLastError();
+    }
+    return ker;
+}
+
 // the n-th upload-done event of a device (created on first use, kept for the context's lifetime)
 int upload_event(DevState& d0, size_t n, cudaEvent_t* ev) {
     while (d0.up_ev.size() <= n) {
@@ -379,7 +399,7 @@ cudaError_t init_devstate(DevState& d, int device) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d.up, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaEventCreate(&d.up_t0);
     if (e == cudaSuccess) e = cudaEventCreate(&d.up_t1);
-    for (int j = 0; j < 5 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
+    for (int j = 0; j < 6 && e == cudaSuccess; j++) e = cudaEventCreate(&d.ev[j]);
     if (e == cudaSuccess) e = cudaHostAlloc((void**)&d.hs, sizeof(HostScalars), cudaHostAllocPortable | cudaHostAllocMapped);
     if (e == cudaSuccess) e = cudaHostGetDevicePointer((void**)&d.hs_dev, d.hs, 0);
     int v = 0;
@@ -643,6 +663,7 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
         a.pos = d.pos.p, a.sk = d.sk.p, a.val = d.val.p, a.cap = j.cap;
         if ((r = enqueue_run(d, p, a, j.wb, j.we, &ctx->timing.kernel_launches))) return r;
         CK(cudaEventRecord(d.ev[2], d.stream));
+        CK(cudaEventRecord(d.ev[5], d.stream));
         return MZ_OK;
     };
     // D2H of chunk c enqueued -> a helper thread waits for it and writes the caller's arrays (delta
@@ -708,11 +729,10 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
             CK(cudaEventSynchronize(d.ev[2]));
             dbg_sync_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - ts0).count();
         }
-        float h2d = 0, ker = 0;
+        float h2d = 0;
         cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
-        cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
         dev_h2d[di] += h2d;
-        dev_ker[di] += ker;
+        dev_ker[di] += chunk_kernel_ms(d, c >= ND ? &ctx->slot(di, slot_of(c - ND)) : nullptr);
         collect_d2h(di, slot_of(c));  // the slot's previous chunk (stream order: it is out)
         uint64_t count = d.hs->count;
         if (d.hs->overflow) {  // capacity estimate too small: redo this chunk with the exact size
@@ -1813,6 +1833,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     const uint64_t ND = ctx->devs.size();
     auto dev_of = [&](uint64_t c) { return (size_t)(c % ND); };
     auto slot_of = [&](uint64_t c) { return (int)((c / ND) % kSlots); };
+    std::vector<float> dev_h2d(ND, 0.f), dev_ker(ND, 0.f), dev_d2h(ND, 0.f);
     struct SyncAll {  // error paths: nothing may still write the caller's arrays
         mz_ctx* ctx;
         ~SyncAll() {
@@ -2065,6 +2086,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         a.out_offsets = d.offs.p;
         if ((r = launch(d, j))) return r;
         CK(cudaEventRecord(d.ev[2], d.stream));
+        CK(cudaEventRecord(d.ev[5], d.stream));
         return MZ_OK;
     };
     // kernel done -> counts known -> D2H of this chunk's outputs and CSR offsets
@@ -2074,11 +2096,10 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         int r;
         CK(cudaSetDevice(d.device));
         CK(cudaStreamSynchronize(d.stream));
-        float h2d = 0, ker = 0;
+        float h2d = 0;
         cudaEventElapsedTime(&h2d, d.ev[0], d.ev[1]);
-        cudaEventElapsedTime(&ker, d.ev[1], d.ev[2]);
-        ctx->timing.h2d_ms += h2d;
-        ctx->timing.kernel_ms += ker;
+        dev_h2d[dev_of(c)] += h2d;
+        dev_ker[dev_of(c)] += chunk_kernel_ms(d, c >= ND ? &ctx->slot(dev_of(c), slot_of(c - ND)) : nullptr);
         if (d.hs->overflow) {  // capacity estimate too small: redo this chunk with the exact size
             j.cap = d.hs->count;
             if ((r = launch(d, j))) return r;
@@ -2126,7 +2147,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         CK(cudaEventSynchronize(d.ev[3]));
         float d2h = 0;
         cudaEventElapsedTime(&d2h, d.ev[2], d.ev[3]);
-        ctx->timing.d2h_ms += d2h;
+        dev_d2h[dev_of(c)] += d2h;
         const uint64_t nr = j.r1 - j.r0;
         const uint64_t* lo = reinterpret_cast<const uint64_t*>(d.st_offs.p);
         for (uint64_t i = 1; i <= nr; i++) out_offsets[j.r0 + i] = j.out_off + lo[i];
@@ -2143,6 +2164,11 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         if (c < nchunks && (rc = issue(c))) return rc;
         if (c >= ND && c - ND < nchunks && (rc = retire(c - ND))) return rc;
         if (c >= 2 * ND && (rc = finish(c - 2 * ND))) return rc;
+    }
+    for (size_t i = 0; i < ND; i++) {  // per-phase times: the busiest device (sums over its chunks)
+        ctx->timing.h2d_ms = std::max(ctx->timing.h2d_ms, dev_h2d[i]);
+        ctx->timing.kernel_ms = std::max(ctx->timing.kernel_ms, dev_ker[i]);
+        ctx->timing.d2h_ms = std::max(ctx->timing.d2h_ms, dev_d2h[i]);
     }
     ctx->timing.total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
     out->count = total;
