@@ -843,6 +843,15 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
     return too_small ? MZ_ERR_CAPACITY : MZ_OK;
 }
 
+// Chunk-local CSR offsets -> global ones (mz_run_batch): the base of a chunk is the number of entries
+// of all chunks before it, known once their kernels have finished.  Done on the device so that the
+// offsets can be copied straight into the caller's array (a host loop over 200 M offsets was a
+// third of config 5's end-to-end time).
+__global__ void mz_rebase_offsets_kernel(unsigned long long* __restrict__ offs, uint64_t n, unsigned long long base) {
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) offs[i] += base;
+}
+
 // Output::values_u64 / values_u128 (src/lib.rs:598-629): one thread per position.
 __global__ void mz_values_kernel(mz::KArgs a, const uint32_t* __restrict__ pos, uint64_t n, uint64_t n_bp,
                                  uint64_t* __restrict__ val, uint32_t* __restrict__ bad) {
@@ -1891,6 +1900,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
     const uint64_t nchunks = (n_reads + chunk_reads - 1) / chunk_reads;
     const bool page_in = is_pageable(packed);
     const bool page_out = is_pageable(out->pos) || (p->want_sk && is_pageable(out->sk)) || (vw && is_pageable(out->val));
+    const bool page_offs = is_pageable(out_offsets);
 
     struct BJob {
         uint64_t r0 = 0, r1 = 0, byte_lo = 0, windows = 0, n_units = 0, cap = 0, count = 0, out_off = 0;
@@ -2116,9 +2126,21 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         total += count;
         if (too_small) return MZ_OK;
         CK(cudaEventRecord(d.ev[2], d.stream));
-        // chunk-local CSR offsets go through pinned memory; the host adds the chunk's base
-        if ((r = d.st_offs.reserve((nr + 1) * 8))) return r;
-        CK(cudaMemcpyAsync(d.st_offs.p, d.offs.p, (nr + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+        // CSR offsets: add the chunk's base on the device, then straight into the caller's array
+        // (through a pinned bounce buffer when that array is pageable)
+        if (j.out_off) {
+            const unsigned nt = 256;
+            mz_rebase_offsets_kernel<<<(unsigned)((nr + 1 + nt - 1) / nt), nt, 0, d.stream>>>(
+                reinterpret_cast<unsigned long long*>(d.offs.p), nr + 1, (unsigned long long)j.out_off);
+            CK(cudaGetLastError());
+            ctx->timing.kernel_launches++;
+        }
+        if (page_offs) {
+            if ((r = d.st_offs.reserve((nr + 1) * 8))) return r;
+            CK(cudaMemcpyAsync(d.st_offs.p, d.offs.p, (nr + 1) * 8, cudaMemcpyDeviceToHost, d.stream));
+        } else {
+            CK(cudaMemcpyAsync(out_offsets + j.r0 + 1, d.offs.p + 1, nr * 8, cudaMemcpyDeviceToHost, d.stream));
+        }
         if (count) {
             uint32_t *hpos = out->pos + j.out_off, *hsk = p->want_sk ? out->sk + j.out_off : nullptr;
             uint64_t* hval = vw ? out->val + j.out_off * vw : nullptr;
@@ -2149,8 +2171,7 @@ int mz_run_batch(mz_ctx* ctx, const mz_params* p, const uint8_t* packed, uint64_
         cudaEventElapsedTime(&d2h, d.ev[2], d.ev[3]);
         dev_d2h[dev_of(c)] += d2h;
         const uint64_t nr = j.r1 - j.r0;
-        const uint64_t* lo = reinterpret_cast<const uint64_t*>(d.st_offs.p);
-        for (uint64_t i = 1; i <= nr; i++) out_offsets[j.r0 + i] = j.out_off + lo[i];
+        if (page_offs) parallel_memcpy(out_offsets + j.r0 + 1, reinterpret_cast<const uint64_t*>(d.st_offs.p) + 1, nr * 8);
         if (j.staged && j.count) {
             parallel_memcpy(out->pos + j.out_off, d.st_pos.p, j.count * 4);
             if (p->want_sk) parallel_memcpy(out->sk + j.out_off, d.st_sk.p, j.count * 4);
