@@ -535,7 +535,7 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
         uint64_t wb, we, cap, byte_lo, count = 0, out_off = 0, abyte_lo = 0;
         size_t nbytes, anbytes = 0;
         bool staged = false;
-        float decode_ms = 0;
+        float decode_ms = 0, t_out_ms = 0;  // MZ_DEBUG_PIPE: decode time, D2H completion since the call began
         const uint8_t* d_in = nullptr;  // this chunk's bytes on its device
         cudaEvent_t up_done = nullptr;  // front-loaded upload: the copy of this chunk has landed
     };
@@ -693,12 +693,14 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
         if (r) return r;
         const bool want_sk = p.want_sk != 0;
         int* const hrc = &helper_rc[hi];
-        auto work = [&d, &j, hrc, out, vw, delta, want_sk, job_threads]() {
+        auto work = [&d, &j, hrc, out, vw, delta, want_sk, job_threads, t_start]() {
             if (cudaSetDevice(d.device) != cudaSuccess || cudaEventSynchronize(d.ev[3]) != cudaSuccess) {
                 *hrc = MZ_ERR_CUDA;
                 return;
             }
             const auto t0 = std::chrono::steady_clock::now();
+            j.t_out_ms = std::chrono::duration<float, std::milli>(t0 - t_start).count();
+            if (getenv("MZ_DEBUG_SKIP_DECODE")) return;  // experiments: is the copy rate the decoders' doing?
             if (delta) {
                 delta_decode(d.st_delta.p, j.count, out->pos + j.out_off, job_threads);
                 if (want_sk) delta_decode(d.st_delta.p + delta_bytes(j.count), j.count, out->sk + j.out_off, job_threads);
@@ -838,6 +840,13 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
         for (size_t i = 0; i < ndev; i++)
             fprintf(stderr, "[mz pipeline]   device %d: h2d %.2f ms, kernels %.2f ms, d2h %.2f ms (sums over its chunks)\n",
                     ctx->devs[i].device, dev_h2d[i], dev_ker[i], dev_d2h[i]);
+        if (atoi(getenv("MZ_DEBUG_PIPE")) > 1) {
+            fprintf(stderr, "[mz pipeline]   D2H of chunk c complete at (ms):");
+            for (const Job& j : jobs) fprintf(stderr, " %.1f", j.t_out_ms);
+            fprintf(stderr, "\n[mz pipeline]   decode of chunk c took (ms):");
+            for (const Job& j : jobs) fprintf(stderr, " %.1f", j.decode_ms);
+            fprintf(stderr, "\n");
+        }
     }
     out->count = total;
     return too_small ? MZ_ERR_CAPACITY : MZ_OK;

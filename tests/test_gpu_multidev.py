@@ -170,6 +170,54 @@ def test_batch_reads_sharded_over_devices(sm, oracle, monkeypatch):
         ctx.close()
 
 
+def test_batch_into_pinned_arrays(sm, oracle, monkeypatch):
+    """Pinned caller arrays (mz_host_alloc): positions AND the CSR offsets are copied straight from
+    the devices to their final place (offsets rebased on the device, no bounce buffer, no host
+    pass) -- the path bench.py's config 5 takes.  Checked against the per-read oracle loop."""
+    import ctypes as C
+    import importlib
+
+    ffi = importlib.import_module("simd-minimizers_b200._ffi")
+    L = ffi.lib()
+    n_reads, read_len, stride = 300_000, 150, 38
+    k, w = 21, 11
+    packed = oracle.synth_packed(5, n_reads * stride * 4 + 64)
+    pr = oracle.make_params(k, w, canonical=True)
+    eo, ep, _, _ = oracle.run_reads(packed, n_reads, stride, read_len, pr, threads=8)
+    nbytes = n_reads * stride
+    cap = len(ep) + 1024
+
+    def pinned(n, dtype):
+        q = C.c_void_p()
+        assert L.mz_host_alloc(C.byref(q), n * np.dtype(dtype).itemsize) == 0
+        arr = np.ctypeslib.as_array(C.cast(q, C.POINTER(C.c_uint8)), shape=(n * np.dtype(dtype).itemsize,)).view(dtype)
+        return q, arr
+
+    q_in, h_in = pinned(nbytes + 64, np.uint8)
+    h_in[:nbytes] = packed.view(np.uint8)[:nbytes]
+    q_off, h_off = pinned(n_reads + 1, np.uint64)
+    q_pos, h_pos = pinned(cap, np.uint32)
+    p = ffi.MzParams()
+    L.mz_params_nthash(C.byref(p), k, w, 0, 1)
+    monkeypatch.setenv("MZ_BATCH_CHUNK_READS", "40009")   # 8 chunks: bases of all sizes to add
+    try:
+        for devs in _device_lists():
+            ctx = sm.Context(devs)
+            h_off[:] = 0xDEADBEEF
+            h_pos[:] = 0xFFFFFFFF
+            out = ffi.MzOut(q_pos.value, None, None, cap, 0)
+            rc = L.mz_run_batch(ctx.handle, C.byref(p), q_in.value, nbytes, n_reads, None, None, stride, read_len,
+                                q_off.value, C.byref(out))
+            assert rc == 0, rc
+            assert out.count == len(ep)
+            assert np.array_equal(h_off, eo), devs
+            assert np.array_equal(h_pos[:len(ep)], ep), devs
+            ctx.close()
+    finally:
+        for q in (q_in, q_off, q_pos):
+            L.mz_host_free(q)
+
+
 def test_pcie_probe(sm):
     """mz_pcie_probe: the measured copy ceiling bench.py reports next to e2e."""
     import ctypes as C
