@@ -44,7 +44,20 @@ constexpr uint32_t FAST_BPS = 1;    // resident blocks per SM
 // e of copy c sits at 16-byte slot e*8 + c: the eight lanes of a quarter warp (one LDS.128 pass)
 // always hit eight different bank groups -> no bank conflicts on the random table lookups.
 constexpr uint32_t FAST_TC = 8;
-constexpr size_t FAST_SMEM_LIMIT = 204 * 1024;  // per block: ~50 KB of L1 stay for the input stream
+// Shared memory per block.  The SM splits 228 KB between shared memory and L1 in steps (0, 8, 16, 32,
+// 64, 100, 132, 164, 196, 228 KB of shared memory), and the carve-out must hold the dynamic request
+// plus 1 KB per block: a request of 205 KB takes the last step and leaves the kernel WITHOUT L1 for
+// its input stream (every lane walks its own cache line: 16 warps x 32 lanes x 128 B = 64 KB of
+// active lines per SM).  Segments that fit 194 KB stay below the 196 KB step and keep 32 KB of L1
+// (C2: 658 -> 714 Gbp/s for the same segments).  Dense outputs, whose segments are cut short by
+// the queue space, do better with all of it (closed syncmers w = 11: 482 with 194 KB, 496 with 204
+// KB at the same slack): they get up to 226 KB.
+constexpr size_t FAST_SMEM_L1 = 194 * 1024;   // leaves 32 KB of L1
+constexpr size_t FAST_SMEM_MAX = 226 * 1024;  // no L1 (sm_100: 227 KB per block at most)
+inline size_t fast_smem_limit(bool keep_l1) {
+    static const size_t env = getenv("MZ_FAST_SMEM_KB") ? (size_t)atoi(getenv("MZ_FAST_SMEM_KB")) * 1024 : 0;
+    return env ? env : (keep_l1 ? FAST_SMEM_L1 : FAST_SMEM_MAX);
+}
 constexpr uint32_t FAST_WARPS = FAST_NT / 32;
 constexpr uint32_t FAST_TOFFS = 36;  // words per warp and buffer: 33 lane offsets (+ padding)
 
@@ -114,11 +127,18 @@ inline uint32_t fast_q_bufs(const mz_params& p) {
     // with l-mer values: closed syncmers w = 11, density 0.18, measured 422 -> 434 Gbp/s with two buffers)
     return fast_density(p) >= (p.mode == MZ_MODE_MINIMIZER ? 0.175 : 0.19) ? 1u : 2u;
 }
-// rows a lane may hold before the warp spills: expected entries of a segment + 6 sigma-ish slack
+// rows a lane may hold before the warp spills: expected entries of a segment + slack.  Queue space is
+// what limits the segment length (and with it the warm-up overhead) and decides whether the block
+// keeps any L1, so the slack is tight: 3 sigma for minimizers, 2 for syncmers (whose sigma below is
+// the Poisson one, an over-estimate).  A lane in ~700 runs over in a tile; the warp then moves its
+// queues to the global spill area and that tile is emitted out of line.  Measured (C2 / closed
+// syncmers w = 11 + u128 values, Gbp/s): 6 sigma 667 / 411, 4: 710 / 460, 3: 716 / 482, 2: 702 / 499,
+// 1.5: 662 / 512, 1: - / 489.
 inline uint32_t fast_q_trig(uint32_t S, const mz_params& p) {
     // (the number of minimizers in S windows has a standard deviation of about sqrt(2 S / 3 w):
     // gaps are close to uniform on 1..w; syncmers: Poisson-like)
-    static const double nsig = getenv("MZ_FAST_QSIGMA") ? atof(getenv("MZ_FAST_QSIGMA")) : 6.0;
+    static const double nsig_env = getenv("MZ_FAST_QSIGMA") ? atof(getenv("MZ_FAST_QSIGMA")) : -1.0;
+    const double nsig = nsig_env >= 0 ? nsig_env : (p.mode == MZ_MODE_MINIMIZER ? 3.0 : 2.0);
     const double mean = S * fast_density(p);
     const double sigma = p.mode == MZ_MODE_MINIMIZER ? sqrt(2.0 * S / (3.0 * p.w)) : sqrt(mean);
     return (uint32_t)std::min<double>(S + 1.0, mean + nsig * sigma + 4.0);
@@ -1083,7 +1103,7 @@ struct FastPlan {
 };
 
 // queue geometry for segments of S windows; false when it does not fit the shared memory
-inline bool fast_queue_plan(uint32_t S, const mz_params& p, FastPlan* pl) {
+inline bool fast_queue_plan(uint32_t S, const mz_params& p, FastPlan* pl, bool keep_l1 = false) {
     const uint32_t sb = fast_sb(fast_wt(p.w));
     pl->S = S;
     pl->lead = fast_lead(p.w);
@@ -1098,7 +1118,7 @@ inline bool fast_queue_plan(uint32_t S, const mz_params& p, FastPlan* pl) {
     const uint32_t elems = pl->nb * sb + 1;
     if (p.w <= FAST_MAX_W ? elems >= 2048 : elems >= 65535) return false;
     pl->q_bufs = fast_q_bufs(p);
-    return fast_smem(p.w, pl->q_rows, pl->q_bufs) <= FAST_SMEM_LIMIT;
+    return fast_smem(p.w, pl->q_rows, pl->q_bufs) <= fast_smem_limit(keep_l1);
 }
 
 // Geometry for the fast kernel; returns false when (k, w, ...) is outside its domain.
@@ -1131,13 +1151,30 @@ inline bool plan_fast(int sm_count, const mz_params& p, uint64_t nwin, FastPlan*
         s = nb * sb - lead;
     }
     s = std::max<uint32_t>(1, s);
-    // the queues live in shared memory: shorten the segments until they fit (dense outputs)
-    while (!fast_queue_plan(s, p, pl)) {
-        if (s <= sb) {
-            if (s <= 1) return false;
-            s = std::max<uint32_t>(1, s / 2);
-        } else {
-            s -= sb;
+    // the queues live in shared memory: shorten the segments until they fit (dense outputs).
+    // First within the budget that keeps 32 KB of L1; when that costs more than a tenth of the
+    // segment length, with all the shared memory there is.
+    auto fit = [&](uint32_t s0, bool keep_l1, FastPlan* out) -> uint32_t {
+        uint32_t q = s0;
+        while (!fast_queue_plan(q, p, out, keep_l1)) {
+            if (q <= sb) {
+                if (q <= 1) return 0;
+                q = std::max<uint32_t>(1, q / 2);
+            } else {
+                q -= sb;
+            }
+        }
+        return q;
+    };
+    const uint32_t s_want = s;
+    s = fit(s_want, true, pl);
+    if (s == 0 || (uint64_t)s * 10 < (uint64_t)s_want * 9) {
+        FastPlan alt = *pl;
+        const uint32_t s2 = fit(s_want, false, &alt);
+        if (s2 == 0 && s == 0) return false;
+        if (s2 > s) {
+            s = s2;
+            *pl = alt;
         }
     }
     const uint64_t Tt = (uint64_t)32 * s;

@@ -53,7 +53,7 @@ int main() {
                     CHECK(w > 32 || pl.nb * sb + 1 < 2048);
                     CHECK(w <= 32 ? mz::fast_qbytes(w) == 2 : mz::fast_qbytes(w) == 4);
                     CHECK(pl.q_rows == pl.q_trig + (w > 32 ? 4 : sb) && pl.q_trig >= 1);  // guard rows between two overflow checks
-                    CHECK((pl.q_bufs == 1 || pl.q_bufs == 2) && mz::fast_smem(w, pl.q_rows, pl.q_bufs) <= mz::FAST_SMEM_LIMIT);
+                    CHECK((pl.q_bufs == 1 || pl.q_bufs == 2) && mz::fast_smem(w, pl.q_rows, pl.q_bufs) <= mz::FAST_SMEM_MAX);
                     CHECK((unsigned long long)pl.num_tiles * 32 * pl.S >= nwin);
                     CHECK(pl.grid >= 1 && pl.grid <= 148 * mz::FAST_BPS);
                     CHECK(pl.scratch_words_per_block == mz::fast_spill_words(pl.S, w));
