@@ -43,7 +43,10 @@ constexpr uint32_t FAST_BPS = 1;    // resident blocks per SM
 // The 256-entry delta table is stored FAST_TC times, copy c = lane & 7 interleaved so that entry
 // e of copy c sits at 16-byte slot e*8 + c: the eight lanes of a quarter warp (one LDS.128 pass)
 // always hit eight different bank groups -> no bank conflicts on the random table lookups.
-constexpr uint32_t FAST_TC = 8;
+#ifndef MZ_FAST_TC
+#define MZ_FAST_TC 8
+#endif
+constexpr uint32_t FAST_TC = MZ_FAST_TC;
 // Shared memory per block.  The SM splits 228 KB between shared memory and L1 in steps (0, 8, 16, 32,
 // 64, 100, 132, 164, 196, 228 KB of shared memory), and the carve-out must hold the dynamic request
 // plus 1 KB per block: a request of 205 KB takes the last step and leaves the kernel WITHOUT L1 for
