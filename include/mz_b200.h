@@ -93,6 +93,13 @@ int mz_device_count(int* n);
  *      CANONICAL flag; the default hasher is NtHasher<CANONICAL> (src/lib.rs:240-321). ---- */
 int mz_params_nthash(mz_params* p, uint32_t k, uint32_t w, uint32_t mode, uint32_t canonical);
 int mz_params_mulhash(mz_params* p, uint32_t k, uint32_t w, uint32_t mode, uint32_t canonical);
+/* Parity status of the built-in tables: the NtHasher tables are pinned by the
+ * reference's own k = 5 vectors (src/lib.rs:92-135); the MulHasher tables, f(b) = b * 0x27220a95
+ * (the low half of the constant at bench/src/rescan_daniel.rs:38) and c(b) = f(b ^ 2), restate
+ * seq-hash 0.2.0, which is not in the reference tree, and are NOT pinned by any reference vector:
+ * tests/test_reference_dump.py derives every hasher's tables from a dump of the real crate
+ * (tools/dump_reference_vectors.rs) and compares.  A caller that has the real hasher object can
+ * always pass its tables with mz_params_set_tables. */
 /* Replace only the hasher of *p (Builder::hasher, src/lib.rs:327-337). hash_canonical is the
  * hasher's own RC flag and may differ from strand_tiebreak (forward builder + canonical hasher,
  * src/minimizers.rs:69-71). */
