@@ -700,7 +700,6 @@ int run_pipelined(mz_ctx* ctx, size_t ndev, const mz_params& p, const uint8_t* p
             }
             const auto t0 = std::chrono::steady_clock::now();
             j.t_out_ms = std::chrono::duration<float, std::milli>(t0 - t_start).count();
-            if (getenv("MZ_DEBUG_SKIP_DECODE")) return;  // experiments: is the copy rate the decoders' doing?
             if (delta) {
                 delta_decode(d.st_delta.p, j.count, out->pos + j.out_off, job_threads);
                 if (want_sk) delta_decode(d.st_delta.p + delta_bytes(j.count), j.count, out->sk + j.out_off, job_threads);

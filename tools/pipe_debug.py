@@ -11,8 +11,8 @@ p = ffi.MzParams(); L.mz_params_nthash(C.byref(p), k, w, 0, 1); p.value_bits = 6
 cap = int(n * 0.1 * 1.1) + 65536
 h_pos = bench.HostBuf(L, ffi, cap * 4, np.uint32); h_val = bench.HostBuf(L, ffi, cap * 8, np.uint64)
 ctx = sm.Context([0])
-for env in ({}, {"MZ_DEBUG_SKIP_DECODE": "1"}, {"MZ_HOST_THREADS": "4"}, {"MZ_NO_FRONT_UPLOAD": "1"}, {"MZ_CHUNK_WINDOWS": "64000000"}, {"MZ_CHUNK_WINDOWS": "260000000"}):
-    for kk in ("MZ_DEBUG_SKIP_DECODE", "MZ_HOST_THREADS", "MZ_NO_FRONT_UPLOAD", "MZ_CHUNK_WINDOWS"): os.environ.pop(kk, None)
+for env in ({}, {"MZ_HOST_THREADS": "4"}, {"MZ_NO_FRONT_UPLOAD": "1"}, {"MZ_CHUNK_WINDOWS": "64000000"}, {"MZ_CHUNK_WINDOWS": "260000000"}):
+    for kk in ("MZ_HOST_THREADS", "MZ_NO_FRONT_UPLOAD", "MZ_CHUNK_WINDOWS"): os.environ.pop(kk, None)
     os.environ.update(env)
     print("==", env, flush=True)
     for it in range(3):
