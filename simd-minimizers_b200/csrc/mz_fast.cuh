@@ -62,6 +62,12 @@ inline size_t fast_smem_limit(bool keep_l1) {
     return env ? env : (keep_l1 ? FAST_SMEM_L1 : FAST_SMEM_MAX);
 }
 constexpr uint32_t FAST_WARPS = FAST_NT / 32;
+// Entries per queue row: the 32 lanes plus one unused entry.  With rows of exactly 64 / 128 bytes the
+// rows of one lane sit in only two banks, and the emission pass, where the 32 lanes of a warp read
+// 32 consecutive rows of the same owner lane, ran into a 16-way bank conflict on every queue load
+// (37 M of the 51 M shared-memory conflicts of an 800 Mbp launch).  Rows of 33 entries walk all
+// 32 banks.  (Costs 3 % of the queue space: C2 715 -> 717, forward k=21 w=11 997 -> 1056 Gbp/s.)
+constexpr uint32_t FAST_ROWENT = 33;
 constexpr uint32_t FAST_TOFFS = 36;  // words per warp and buffer: 33 lane offsets (+ padding)
 
 // Small windows: several van-Herk blocks (B of them, B*W <= 32 k-mers) share one loop iteration, so
@@ -112,7 +118,7 @@ inline size_t fast_spill_words(uint32_t S, uint32_t w) {
 // shared memory: table | misc | per warp: lane offsets (2 tiles in flight) | queues (2 tiles in flight)
 inline size_t fast_smem(uint32_t w, uint32_t q_rows, uint32_t q_bufs = 2) {
     return 256 * FAST_TC * 16 + 64 +
-           (size_t)FAST_WARPS * (2 * FAST_TOFFS * 4 + (size_t)q_bufs * q_rows * 32 * fast_qbytes(w));
+           (size_t)FAST_WARPS * (2 * FAST_TOFFS * 4 + (size_t)q_bufs * q_rows * FAST_ROWENT * fast_qbytes(w));
 }
 inline double fast_density(const mz_params& p) {
     return p.mode == MZ_MODE_MINIMIZER ? 2.0 / (p.w + 1.0)
@@ -246,10 +252,10 @@ __device__ __forceinline__ void q_push4_ne_fma(uint32_t& qa, uint32_t prev, cons
         asm volatile(
             "{\n\t.reg .pred p0, p1, p2, p3;\n\t"
             "setp.ne.u32 p0, %1, %9;\n\tsetp.ne.u32 p1, %2, %1;\n\tsetp.ne.u32 p2, %3, %2;\n\tsetp.ne.u32 p3, %4, %3;\n\t"
-            "@p0 st.shared.u32 [%0], %5;\n\t@p0 mad.lo.u32 %0, %10, 128, %0;\n\t"
-            "@p1 st.shared.u32 [%0], %6;\n\t@p1 mad.lo.u32 %0, %10, 128, %0;\n\t"
-            "@p2 st.shared.u32 [%0], %7;\n\t@p2 mad.lo.u32 %0, %10, 128, %0;\n\t"
-            "@p3 st.shared.u32 [%0], %8;\n\t@p3 mad.lo.u32 %0, %10, 128, %0;\n\t}"
+            "@p0 st.shared.u32 [%0], %5;\n\t@p0 mad.lo.u32 %0, %10, 132, %0;\n\t"
+            "@p1 st.shared.u32 [%0], %6;\n\t@p1 mad.lo.u32 %0, %10, 132, %0;\n\t"
+            "@p2 st.shared.u32 [%0], %7;\n\t@p2 mad.lo.u32 %0, %10, 132, %0;\n\t"
+            "@p3 st.shared.u32 [%0], %8;\n\t@p3 mad.lo.u32 %0, %10, 132, %0;\n\t}"
             : "+r"(qa)
             : "r"(r[0]), "r"(NG > 1 ? r[1] : r[0]), "r"(NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0])),
               "r"(NG > 3 ? r[3] : (NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0]))), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]),
@@ -259,10 +265,10 @@ __device__ __forceinline__ void q_push4_ne_fma(uint32_t& qa, uint32_t prev, cons
             "{\n\t.reg .pred p0, p1, p2, p3;\n\t.reg .b16 l0, l1, l2, l3;\n\t"
             "setp.ne.u32 p0, %1, %9;\n\tsetp.ne.u32 p1, %2, %1;\n\tsetp.ne.u32 p2, %3, %2;\n\tsetp.ne.u32 p3, %4, %3;\n\t"
             "cvt.u16.u32 l0, %5;\n\tcvt.u16.u32 l1, %6;\n\tcvt.u16.u32 l2, %7;\n\tcvt.u16.u32 l3, %8;\n\t"
-            "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %10, 64, %0;\n\t"
-            "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %10, 64, %0;\n\t"
-            "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %10, 64, %0;\n\t"
-            "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %10, 64, %0;\n\t}"
+            "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %10, 66, %0;\n\t"
+            "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %10, 66, %0;\n\t"
+            "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %10, 66, %0;\n\t"
+            "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %10, 66, %0;\n\t}"
             : "+r"(qa)
             : "r"(r[0]), "r"(NG > 1 ? r[1] : r[0]), "r"(NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0])),
               "r"(NG > 3 ? r[3] : (NG > 2 ? r[2] : (NG > 1 ? r[1] : r[0]))), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]),
@@ -282,10 +288,10 @@ __device__ __forceinline__ void q_push4_mask_fma(uint32_t& qa, const uint32_t (&
         "and.b32 t0, t0, 1;\n\tand.b32 t1, t1, 1;\n\tand.b32 t2, t2, 1;\n\tand.b32 t3, t3, 1;\n\t"
         "setp.ne.u32 p0, t0, 0;\n\tsetp.ne.u32 p1, t1, 0;\n\tsetp.ne.u32 p2, t2, 0;\n\tsetp.ne.u32 p3, t3, 0;\n\t"
         "cvt.u16.u32 l0, %5;\n\tcvt.u16.u32 l1, %6;\n\tcvt.u16.u32 l2, %7;\n\tcvt.u16.u32 l3, %8;\n\t"
-        "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %9, 64, %0;\n\t"
-        "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %9, 64, %0;\n\t"
-        "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %9, 64, %0;\n\t"
-        "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %9, 64, %0;\n\t}"
+        "@p0 st.shared.u16 [%0], l0;\n\t@p0 mad.lo.u32 %0, %9, 66, %0;\n\t"
+        "@p1 st.shared.u16 [%0], l1;\n\t@p1 mad.lo.u32 %0, %9, 66, %0;\n\t"
+        "@p2 st.shared.u16 [%0], l2;\n\t@p2 mad.lo.u32 %0, %9, 66, %0;\n\t"
+        "@p3 st.shared.u16 [%0], l3;\n\t@p3 mad.lo.u32 %0, %9, 66, %0;\n\t}"
         : "+r"(qa)
         : "r"(m[0]), "r"(m[1]), "r"(m[2]), "r"(m[3]), "r"(e[0]), "r"(e[1]), "r"(e[2]), "r"(e[3]), "r"(one));
 }
@@ -387,7 +393,7 @@ __device__ __forceinline__ void fast_emit_tile(const KArgs& a, uint32_t tile, un
     // qs = shared address of the tile's queue rows: entry i of lane t at qs + i * ROWB + t * sizeof(QT)
     // tp_s = shared address of the 33 lane offsets
     using QT = typename std::conditional<XW, uint32_t, uint16_t>::type;
-    constexpr uint32_t DBITS = XW ? 8 : 5, DMASK = (1u << DBITS) - 1u, ROWB = 32 * sizeof(QT);
+    constexpr uint32_t DBITS = XW ? 8 : 5, DMASK = (1u << DBITS) - 1u, ROWB = FAST_ROWENT * sizeof(QT);
     constexpr int NW = VB == 64 ? 3 : VB == 128 ? 5 : 0;
     const uint32_t lane = threadIdx.x & 31u;
     const uint32_t Wr = a.w, S = a.S, len = a.val_len;
@@ -612,7 +618,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
     constexpr int SB = B * W;            // k-mers per loop iteration (<= 32)
     constexpr uint32_t NT = FAST_NT;
     using QT = typename std::conditional<XW, uint32_t, uint16_t>::type;
-    constexpr int ROWB = 32 * (int)sizeof(QT);            // bytes per queue row
+    constexpr int ROWB = (int)FAST_ROWENT * (int)sizeof(QT);  // bytes per queue row
     constexpr uint32_t DBITS = XW ? 8 : 5, DMUL = (1u << DBITS) - 1u;  // entry = pos << DBITS | (window end - pos)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
@@ -666,7 +672,7 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
     // opaque 1 for imad(): a kernel argument, so that ptxas cannot fold x * 1 + c back into an
     // ALU-pipe add (the positions and the queue pointer are bumped on the idle FMA pipe)
     const uint32_t one = a.one;
-    static_assert(ROWB == (XW ? 128 : 64), "q_push4_ne_fma hard-codes the row size");
+    static_assert(ROWB == (XW ? 132 : 66), "q_push4_ne_fma / q_push4_mask_fma hard-code the row size");
     // syncmer offsets d = (window end) - (selected pos): closed {0, W-1}, open {(W-1)/2}
     const uint32_t so1 = a.mode == MODE_CLOSED ? 0u : (Wr - 1) / 2, so2 = a.mode == MODE_CLOSED ? Wr - 1 : (Wr - 1) / 2;
     const uint32_t smask = (1u << (so1 & 31u)) | (1u << (so2 & 31u));  // !XW: bit d set <=> syncmer
