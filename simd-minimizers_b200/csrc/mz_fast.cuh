@@ -43,6 +43,9 @@ constexpr uint32_t FAST_BPS = 1;    // resident blocks per SM
 // The 256-entry delta table is stored FAST_TC times, copy c = lane & 7 interleaved so that entry
 // e of copy c sits at 16-byte slot e*8 + c: the eight lanes of a quarter warp (one LDS.128 pass)
 // always hit eight different bank groups -> no bank conflicts on the random table lookups.
+#ifndef MZ_FAST_TD
+#define MZ_FAST_TD 2
+#endif
 #ifndef MZ_FAST_TC
 #define MZ_FAST_TC 8
 #endif
@@ -835,6 +838,10 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                 }
                 // Two k-mers per step: one table load gives both hashes; the prefix minimum and
                 // the first window of the pair use the 3-input VIMNMX3.
+                constexpr int TD = MZ_FAST_TD;  // table lookups in flight (pairs ahead)
+                uint4 tq[TD];
+#pragma unroll
+                for (int d = 0; d < TD; d++) tq[d] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
                 for (int t = 0; t < W; t += 2) {
                     const bool two = t + 1 < W;
@@ -860,12 +867,27 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                             }
                         }
                     }
-                    const uint32_t word = N[(t >> 4) * 2 + ((t >> 1) & 1)];
-                    const uint32_t idx = get_byte(word, (t & 15) >> 2);
-                    const uint32_t addr = idx * (16u * FAST_TC) + tb;
+                    // table entry of this pair (requested one pair ahead: the lookup only depends on
+                    // the block's base bytes, and its latency is the main loop's largest stall)
+                    auto lookup = [&](int tt) -> uint4 {
+                        const uint32_t word = N[(tt >> 4) * 2 + ((tt >> 1) & 1)];
+                        const uint32_t idx = get_byte(word, (tt & 15) >> 2);
+                        const uint32_t addr = idx * (16u * FAST_TC) + tb;
+                        if (HC) return lds128(addr);
+                        const uint2 e2 = lds64(addr);
+                        return make_uint4(e2.x, e2.y, 0u, 0u);
+                    };
+                    if (t == 0) {
+#pragma unroll
+                        for (int d = 0; d < TD; d++)
+                            if (2 * d < W) tq[d] = lookup(2 * d);
+                    }
+                    const uint4 e = tq[0];
+#pragma unroll
+                    for (int d = 0; d + 1 < TD; d++) tq[d] = tq[d + 1];
+                    if (t + 2 * TD < W) tq[TD - 1] = lookup(t + 2 * TD);
                     uint32_t h0, h1 = 0;
                     if (HC) {
-                        const uint4 e = lds128(addr);
                         const uint32_t fA = rotl32(fw, R) ^ e.x, rA = rotr32(rc, R) ^ e.z;
                         h0 = fA + rA;
                         if (two) {
@@ -877,7 +899,6 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                             rc = rA;
                         }
                     } else {
-                        const uint2 e = lds64(addr);
                         const uint32_t fA = rotl32(fw, R) ^ e.x;
                         h0 = fA;
                         if (two) {
