@@ -877,15 +877,21 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                         const uint2 e2 = lds64(addr);
                         return make_uint4(e2.x, e2.y, 0u, 0u);
                     };
-                    if (t == 0) {
+                    // (long-window instances have no registers to spare for the queue: w = 201 60 -> 53 Gbp/s)
+                    uint4 e;
+                    if (XW) {
+                        e = lookup(t);
+                    } else {
+                        if (t == 0) {
 #pragma unroll
-                        for (int d = 0; d < TD; d++)
-                            if (2 * d < W) tq[d] = lookup(2 * d);
+                            for (int d = 0; d < TD; d++)
+                                if (2 * d < W) tq[d] = lookup(2 * d);
+                        }
+                        e = tq[0];
+#pragma unroll
+                        for (int d = 0; d + 1 < TD; d++) tq[d] = tq[d + 1];
+                        if (t + 2 * TD < W) tq[TD - 1] = lookup(t + 2 * TD);
                     }
-                    const uint4 e = tq[0];
-#pragma unroll
-                    for (int d = 0; d + 1 < TD; d++) tq[d] = tq[d + 1];
-                    if (t + 2 * TD < W) tq[TD - 1] = lookup(t + 2 * TD);
                     uint32_t h0, h1 = 0;
                     if (HC) {
                         const uint32_t fA = rotl32(fw, R) ^ e.x, rA = rotr32(rc, R) ^ e.z;
