@@ -877,9 +877,11 @@ __global__ void __launch_bounds__(FAST_NT, FAST_BPS) mz_fast_kernel(const __grid
                         const uint2 e2 = lds64(addr);
                         return make_uint4(e2.x, e2.y, 0u, 0u);
                     };
-                    // (long-window instances have no registers to spare for the queue: w = 201 60 -> 53 Gbp/s)
+                    // (instances that have no registers to spare for the queue look up just in time: long
+                    // windows, w = 201 60 -> 53 Gbp/s with the queue; strand-aware kernels with two suffix
+                    // arrays of more than 26 registers each, k = 11 w = 31 463 -> 450)
                     uint4 e;
-                    if (XW) {
+                    if (XW || (LR && W > 26)) {
                         e = lookup(t);
                     } else {
                         if (t == 0) {
