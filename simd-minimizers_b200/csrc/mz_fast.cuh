@@ -6,14 +6,14 @@
 //   * the words holding the entering- and leaving-base streams were prefetched one block ahead;
 //     they are re-aligned with funnel shifts and interleaved so that every byte holds
 //     (in,in,out,out) of two consecutive bases;
-//   * one LDS.128 from a 256-entry table returns the rolling-hash deltas of BOTH bases for the
-//     forward and the reverse-complement hash (ntHash/mulHash are GF(2)-linear in the tables),
-//     so a k-mer hash costs SHF+LOP3 per strand;
+//   * one LDS.128 from a 256-entry table (requested two pairs of k-mers ahead) returns the
+//     rolling-hash deltas of BOTH bases for the forward and the reverse-complement hash
+//     (ntHash/mulHash are GF(2)-linear in the tables), so a k-mer hash costs SHF+LOP3 per strand;
 //   * (hash & 0xffff0000) | pos goes through a prefix-min / suffix-min pair whose W-entry suffix
 //     array lives in registers (static indexing); the rightmost minimum uses max on the
 //     complemented key, exactly the reference's packing (src/sliding_min.rs:190-195,336-341);
-//   * leftmost != rightmost (1.2e-4 of windows) is tested per pair of windows with two LOP3; the
-//     strand rule (src/canonical.rs) runs out of line for those windows only;
+//   * leftmost != rightmost (1.2e-4 of windows) is tested per group of four windows; the strand
+//     rule (src/canonical.rs) runs out of line for those groups only;
 //   * a window whose selection differs from the previous window's (src/collect.rs:39-76) pushes ONE
 //     16-bit entry -- (selected k-mer << 5 | distance to the window end), built by a single IMAD --
 //     onto the lane's queue in shared memory with a predicated store: nothing is recorded for the
@@ -22,6 +22,9 @@
 // decoupled look-back over tile descriptors (resolved one tile later, so predecessors have
 // published), and one software-pipelined pass in which lane x & 31 handles output entry x (owner
 // lane found by walking the 33 lane offsets, k-mer words fetched one entry ahead).
+// Shared memory is planned against the carve-out steps of the SM (194 KB keeps 32 KB of L1 for the
+// input stream; dense outputs take all 226 KB), queue rows hold 33 entries so that the rows of one
+// lane walk all banks.
 #pragma once
 #include "../../include/mz_b200.h"
 #include <algorithm>
